@@ -78,8 +78,8 @@ def test_stoi_identity_and_short():
 
 def test_selection_hysteresis_is_not_argmax():
     pts = [{"i": i} for i in range(4)]
-    sc = [{"stoi": 0.5, "pesq": 2.0, "snr": 1.0}, {"stoi": 0.5000008, "pesq": 2.0005, "snr": 2.0},
-          None, {"stoi": 0.5000009, "pesq": 2.0009, "snr": 3.0}]
+    sc = [{"stoi": 0.5, "pesq": 2.0, "snr": 1.0}, {"stoi": 0.5000008, "pesq": 2.00005, "snr": 2.0},
+          None, {"stoi": 0.5000009, "pesq": 2.00008, "snr": 3.0}]
     best = select_best(pts, sc)
     assert best["stoi"]["index"] == 0 and best["pesq"]["index"] == 0 and best["balance"]["index"] == 0
     sc[3] = {"stoi": 0.5000011, "pesq": 2.0011, "snr": 3.0}
