@@ -1,0 +1,117 @@
+// Common definitions for the cse kernels (sm_100a; also built by g++ under CSE_EMU for tests).
+#pragma once
+#ifdef CSE_EMU
+#include "cuda_emu.h"
+#else
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#define CSE_LAUNCH(kern, grid, block, smem, stream, ...) \
+    kern<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__)
+#define CSE_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
+#include "../../include/cse.h"
+
+#ifdef CSE_FP64
+typedef double real;
+typedef double2 real2;
+#define CSE_REAL_BITS 64
+#else
+typedef float real;
+typedef float2 real2;
+#define CSE_REAL_BITS 32
+#endif
+#define R(x) ((real)(x))
+#define CSE_HD __host__ __device__ __forceinline__
+#define CSE_D __device__ __forceinline__
+
+CSE_HD real2 mk2(real a, real b) { real2 r; r.x = a; r.y = b; return r; }
+CSE_HD real2 cadd(real2 a, real2 b) { return mk2(a.x + b.x, a.y + b.y); }
+CSE_HD real2 csub(real2 a, real2 b) { return mk2(a.x - b.x, a.y - b.y); }
+CSE_HD real2 cmul(real2 a, real2 b) { return mk2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+CSE_HD real2 cmulc(real2 a, real2 b) { /* a * conj(b) */ return mk2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
+CSE_HD real2 cconj(real2 a) { return mk2(a.x, -a.y); }
+
+// precision-generic math (float intrinsics only where their error is far below the 1e-4 budget)
+#ifdef CSE_FP64
+CSE_HD real r_sqrt(real x) { return sqrt(x); }
+CSE_HD real r_exp(real x) { return exp(x); }
+CSE_HD real r_log(real x) { return log(x); }
+CSE_HD real r_log10(real x) { return log10(x); }
+CSE_HD real r_pow(real x, real y) { return pow(x, y); }
+CSE_HD real r_abs(real x) { return fabs(x); }
+CSE_HD real r_max(real a, real b) { return fmax(a, b); }
+CSE_HD real r_min(real a, real b) { return fmin(a, b); }
+CSE_HD real r_floor(real x) { return floor(x); }
+CSE_HD real r_fma(real a, real b, real c) { return fma(a, b, c); }
+#else
+CSE_HD real r_sqrt(real x) { return sqrtf(x); }
+CSE_HD real r_exp(real x) { return expf(x); }
+CSE_HD real r_log(real x) { return logf(x); }
+CSE_HD real r_log10(real x) { return log10f(x); }
+CSE_HD real r_pow(real x, real y) { return powf(x, y); }
+CSE_HD real r_abs(real x) { return fabsf(x); }
+CSE_HD real r_max(real a, real b) { return fmaxf(a, b); }
+CSE_HD real r_min(real a, real b) { return fminf(a, b); }
+CSE_HD real r_floor(real x) { return floorf(x); }
+CSE_HD real r_fma(real a, real b, real c) { return fmaf(a, b, c); }
+#endif
+// numpy's maximum/minimum/clip propagate NaN, fmax/fmin drop it.  The reference relies on
+// that only through np.nan_to_num, which the gain kernels restate explicitly.
+CSE_HD real r_clip(real x, real lo, real hi) { return r_min(r_max(x, lo), hi); }
+CSE_HD bool r_finite(real x) { return (x - x) == R(0); }
+
+// ---------------------------------------------------------------- geometry helpers
+static inline int cse_ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
+CSE_HD int cse_nbp(int n_fft) { return ((n_fft / 2 + 1) + 7) & ~7; }   // bins padded to 8
+
+// ---------------------------------------------------------------- constant tables
+// One blob in device memory, filled by cse_tables_init.  Offsets in units of `real`.
+#define CSE_TW_N 8192                 // twiddle table: W_8192^k = exp(-2*pi*i*k/8192), k < 4096
+#define CSE_MAX_NFFT 2048
+#define CSE_RS_TAPS 581               // STOI 16k->10k resampler (pystoi resample_oct)
+#define CSE_RS_PHASES 5
+#define CSE_RS_PHASE_TAPS 120         // 117 taps per output phase, padded to 8 x 15
+struct CseTables {
+    real2 tw[CSE_TW_N / 2];
+    real hann256[256], hann512[512], hann1024[1024], hann2048[2048];   // periodic Hann (librosa)
+    real stoi_win[256];                                                 // np.hanning(258)[1:-1]
+    real rs[CSE_RS_PHASES][CSE_RS_PHASE_TAPS];                          // polyphase taps, see k_score
+    int rs_i0[CSE_RS_PHASES + 3];                                       // first input offset per phase
+};
+CSE_D const real* cse_hann(const CseTables* T, int n_fft) {
+    return n_fft == 256 ? T->hann256 : n_fft == 512 ? T->hann512 : n_fft == 1024 ? T->hann1024 : T->hann2048;
+}
+
+// ---------------------------------------------------------------- block reductions
+CSE_D real warp_sum(real v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+CSE_D double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// Sum over the block; result valid in every thread.  `scratch` >= 33 elements of shared memory.
+// blockDim.x must be a multiple of 32.
+template <class T> CSE_D T block_sum(T v, T* scratch) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        T s = lane < nw ? scratch[lane] : (T)0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) scratch[32] = s;
+    }
+    __syncthreads();
+    return scratch[32];
+}

@@ -1,0 +1,166 @@
+// Block-cooperative in-place FFTs in shared memory.
+//
+// Two mirrored radix-2 flow graphs, executed three stages at a time in registers (radix-8
+// passes, one __syncthreads per pass):
+//   fft_dif<LOG2N, INV>  natural-order input  -> bit-reversed output
+//   fft_dit<LOG2N, INV>  bit-reversed input   -> natural-order output
+// (INV=false: forward e^-j; INV=true: unnormalised inverse e^+j)
+// Neither needs a reordering pass: the real-FFT split steps and the frequency-domain products
+// that sit between them address elements through __brev().  Several transforms ("batches")
+// laid out back to back are processed by one call so that every thread has butterflies to do.
+//
+// Storage index of logical element i is SIDX(i) = i + (i >> 3): one pad slot per 8 complex
+// values makes the last pass (thread owns 8 consecutive elements) and the strided middle
+// passes conflict-free for 8-byte accesses.
+#pragma once
+#include "cse_common.cuh"
+
+#define SIDX(i) ((i) + ((i) >> 3))
+#define CSE_FFT_STRIDE(n) ((n) + ((n) >> 3))
+
+CSE_D real2 tw_load(const real2* __restrict__ tw, int idx) {
+#ifdef CSE_EMU
+    return tw[idx];
+#else
+    return __ldg(tw + idx);
+#endif
+}
+
+// W_8^m for m = 0..3 applied to d
+template <int m> CSE_D real2 rot8(real2 d) {
+    const real h = R(0.70710678118654752440);
+    if (m == 0) return d;
+    if (m == 1) return mk2((d.x + d.y) * h, (d.y - d.x) * h);     // * (1 - i)/sqrt2
+    if (m == 2) return mk2(d.y, -d.x);                             // * (-i)
+    return mk2((d.y - d.x) * h, -(d.x + d.y) * h);                 // * (-1 - i)/sqrt2
+}
+template <int m> CSE_D real2 rot8c(real2 d) {   // conj(W_8^m)
+    const real h = R(0.70710678118654752440);
+    if (m == 0) return d;
+    if (m == 1) return mk2((d.x - d.y) * h, (d.x + d.y) * h);     // * (1 + i)/sqrt2
+    if (m == 2) return mk2(-d.y, d.x);                             // * (+i)
+    return mk2(-(d.x + d.y) * h, (d.x - d.y) * h);                 // * (-1 + i)/sqrt2
+}
+
+template <bool CONJ> CSE_D real2 twmul(real2 a, real2 w) { return CONJ ? cmulc(a, w) : cmul(a, w); }
+template <int m, bool CONJ> CSE_D real2 rotf(real2 d) { return CONJ ? rot8c<m>(d) : rot8<m>(d); }
+
+// One pass of RL fused DIF stages (CONJ: conjugated twiddles = inverse transform).  `h` = half size of the first fused stage,
+// q = h >> (RL-1) = smallest butterfly distance of the pass.
+template <int LOG2N, int RL, bool CONJ>
+CSE_D void dif_pass(real2* s, int nbatch, int bstride, int h, const real2* __restrict__ tw, int tid, int nth) {
+    constexpr int N = 1 << LOG2N;
+    constexpr int NB = 1 << RL;               // elements per butterfly
+    const int q = h >> (RL - 1);
+    const int per = N / NB;
+    const int total = nbatch * per;
+    const int twstep = (CSE_TW_N / 2) / h;    // W_{2h}^p = W_T^{p * T/(2h)}
+    for (int idx = tid; idx < total; idx += nth) {
+        const int b = idx / per, r = idx - b * per;
+        const int j = r & (q - 1), grp = r / q;
+        real2* p = s + b * bstride;
+        const int base = grp * (q * NB) + j;
+        real2 v[NB];
+#pragma unroll
+        for (int m = 0; m < NB; ++m) v[m] = p[SIDX(base + m * q)];
+        if (RL == 3) {
+            const real2 w1 = tw_load(tw, j * twstep), w2 = tw_load(tw, j * twstep * 2), w3 = tw_load(tw, j * twstep * 4);
+            real2 d;
+            d = csub(v[0], v[4]); v[0] = cadd(v[0], v[4]); v[4] = twmul<CONJ>(rotf<0, CONJ>(d), w1);
+            d = csub(v[1], v[5]); v[1] = cadd(v[1], v[5]); v[5] = twmul<CONJ>(rotf<1, CONJ>(d), w1);
+            d = csub(v[2], v[6]); v[2] = cadd(v[2], v[6]); v[6] = twmul<CONJ>(rotf<2, CONJ>(d), w1);
+            d = csub(v[3], v[7]); v[3] = cadd(v[3], v[7]); v[7] = twmul<CONJ>(rotf<3, CONJ>(d), w1);
+#pragma unroll
+            for (int g = 0; g < 8; g += 4) {
+                d = csub(v[g], v[g + 2]); v[g] = cadd(v[g], v[g + 2]); v[g + 2] = twmul<CONJ>(d, w2);
+                d = csub(v[g + 1], v[g + 3]); v[g + 1] = cadd(v[g + 1], v[g + 3]); v[g + 3] = twmul<CONJ>(rotf<2, CONJ>(d), w2);
+            }
+#pragma unroll
+            for (int g = 0; g < 8; g += 2) { d = csub(v[g], v[g + 1]); v[g] = cadd(v[g], v[g + 1]); v[g + 1] = twmul<CONJ>(d, w3); }
+        } else if (RL == 2) {
+            const real2 w1 = tw_load(tw, j * twstep), w2 = tw_load(tw, j * twstep * 2);
+            real2 d;
+            d = csub(v[0], v[2]); v[0] = cadd(v[0], v[2]); v[2] = twmul<CONJ>(d, w1);
+            d = csub(v[1], v[3]); v[1] = cadd(v[1], v[3]); v[3] = twmul<CONJ>(rotf<2, CONJ>(d), w1);
+            d = csub(v[0], v[1]); v[0] = cadd(v[0], v[1]); v[1] = twmul<CONJ>(d, w2);
+            d = csub(v[2], v[3]); v[2] = cadd(v[2], v[3]); v[3] = twmul<CONJ>(d, w2);
+        } else {
+            const real2 w1 = tw_load(tw, j * twstep);
+            real2 d = csub(v[0], v[1]); v[0] = cadd(v[0], v[1]); v[1] = twmul<CONJ>(d, w1);
+        }
+#pragma unroll
+        for (int m = 0; m < NB; ++m) p[SIDX(base + m * q)] = v[m];
+    }
+}
+
+// One pass of RL fused DIT stages; q = half size of the FIRST (smallest) fused stage.
+template <int LOG2N, int RL, bool CONJ>
+CSE_D void dit_pass(real2* s, int nbatch, int bstride, int q, const real2* __restrict__ tw, int tid, int nth) {
+    constexpr int N = 1 << LOG2N;
+    constexpr int NB = 1 << RL;
+    const int per = N / NB;
+    const int total = nbatch * per;
+    const int twq = (CSE_TW_N / 2) / q;       // W_{2q}^p = W_T^{p * T/(2q)}
+    for (int idx = tid; idx < total; idx += nth) {
+        const int b = idx / per, r = idx - b * per;
+        const int j = r & (q - 1), grp = r / q;
+        real2* p = s + b * bstride;
+        const int base = grp * (q * NB) + j;
+        real2 v[NB];
+#pragma unroll
+        for (int m = 0; m < NB; ++m) v[m] = p[SIDX(base + m * q)];
+        if (RL == 3) {
+            // distances q (W_{2q}^j), 2q (W_{4q}^{j + (m&1)q}), 4q (W_{8q}^{j + (m&3)q}); conjugated
+            const real2 w3 = tw_load(tw, j * twq), w2 = tw_load(tw, j * (twq >> 1)), w1 = tw_load(tw, j * (twq >> 2));
+            real2 t;
+#pragma unroll
+            for (int g = 0; g < 8; g += 2) { t = twmul<CONJ>(v[g + 1], w3); v[g + 1] = csub(v[g], t); v[g] = cadd(v[g], t); }
+#pragma unroll
+            for (int g = 0; g < 8; g += 4) {
+                t = twmul<CONJ>(v[g + 2], w2); v[g + 2] = csub(v[g], t); v[g] = cadd(v[g], t);
+                t = rotf<2, CONJ>(twmul<CONJ>(v[g + 3], w2)); v[g + 3] = csub(v[g + 1], t); v[g + 1] = cadd(v[g + 1], t);
+            }
+            t = rotf<0, CONJ>(twmul<CONJ>(v[4], w1)); v[4] = csub(v[0], t); v[0] = cadd(v[0], t);
+            t = rotf<1, CONJ>(twmul<CONJ>(v[5], w1)); v[5] = csub(v[1], t); v[1] = cadd(v[1], t);
+            t = rotf<2, CONJ>(twmul<CONJ>(v[6], w1)); v[6] = csub(v[2], t); v[2] = cadd(v[2], t);
+            t = rotf<3, CONJ>(twmul<CONJ>(v[7], w1)); v[7] = csub(v[3], t); v[3] = cadd(v[3], t);
+        } else if (RL == 2) {
+            const real2 w2 = tw_load(tw, j * twq), w1 = tw_load(tw, j * (twq >> 1));
+            real2 t;
+            t = twmul<CONJ>(v[1], w2); v[1] = csub(v[0], t); v[0] = cadd(v[0], t);
+            t = twmul<CONJ>(v[3], w2); v[3] = csub(v[2], t); v[2] = cadd(v[2], t);
+            t = twmul<CONJ>(v[2], w1); v[2] = csub(v[0], t); v[0] = cadd(v[0], t);
+            t = rotf<2, CONJ>(twmul<CONJ>(v[3], w1)); v[3] = csub(v[1], t); v[1] = cadd(v[1], t);
+        } else {
+            const real2 w1 = tw_load(tw, j * twq);
+            real2 t = twmul<CONJ>(v[1], w1); v[1] = csub(v[0], t); v[0] = cadd(v[0], t);
+        }
+#pragma unroll
+        for (int m = 0; m < NB; ++m) p[SIDX(base + m * q)] = v[m];
+    }
+}
+
+// Decimation-in-frequency transform, natural-order in -> bit-reversed out.  INV=false: forward
+// (e^-j); INV=true: unnormalised inverse (e^+j).  Ends with a __syncthreads().
+template <int LOG2N, bool INV>
+CSE_D void fft_dif(real2* s, int nbatch, int bstride, const real2* __restrict__ tw, int tid, int nth) {
+    constexpr int REM = LOG2N % 3;
+    int h = 1 << (LOG2N - 1);
+    if (REM == 1) { dif_pass<LOG2N, 1, INV>(s, nbatch, bstride, h, tw, tid, nth); __syncthreads(); h >>= 1; }
+    if (REM == 2) { dif_pass<LOG2N, 2, INV>(s, nbatch, bstride, h, tw, tid, nth); __syncthreads(); h >>= 2; }
+#pragma unroll
+    for (int p = 0; p < LOG2N / 3; ++p) { dif_pass<LOG2N, 3, INV>(s, nbatch, bstride, h, tw, tid, nth); __syncthreads(); h >>= 3; }
+}
+
+// Decimation-in-time transform, bit-reversed in -> natural-order out.  Ends with a __syncthreads().
+template <int LOG2N, bool INV>
+CSE_D void fft_dit(real2* s, int nbatch, int bstride, const real2* __restrict__ tw, int tid, int nth) {
+    constexpr int REM = LOG2N % 3;
+    int q = 1;
+#pragma unroll
+    for (int p = 0; p < LOG2N / 3; ++p) { dit_pass<LOG2N, 3, INV>(s, nbatch, bstride, q, tw, tid, nth); __syncthreads(); q <<= 3; }
+    if (REM == 2) { dit_pass<LOG2N, 2, INV>(s, nbatch, bstride, q, tw, tid, nth); __syncthreads(); }
+    if (REM == 1) { dit_pass<LOG2N, 1, INV>(s, nbatch, bstride, q, tw, tid, nth); __syncthreads(); }
+}
+
+CSE_D int brev_n(int k, int log2n) { return (int)(__brev((unsigned)k) >> (32 - log2n)); }

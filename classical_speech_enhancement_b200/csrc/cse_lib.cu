@@ -1,0 +1,152 @@
+// libcse_sm100a: C ABI (include/cse.h) over the hand-written kernels.
+// Built for sm_100a by nvcc (build.py) and, for CPU-side kernel tests only, by g++ with
+// -DCSE_EMU (tests/emu).  Host code here only validates arguments, sizes launches and
+// enqueues kernels on the caller's stream; it never allocates or synchronises.
+#define CSE_EMU_IMPL
+#include "cse_common.cuh"
+#include "k_stft.cuh"
+#include "k_enhance.cuh"
+#include "k_noise.cuh"
+#include "k_score.cuh"
+
+#include <mutex>
+#include <cstdarg>
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+static int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(CSE_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+    return CSE_OK;
+}
+static bool valid_nfft(int n_fft) { return n_fft == 256 || n_fft == 512 || n_fft == 1024 || n_fft == 2048; }
+#define CSE_REQUIRE(cond, ...) do { if (!(cond)) return fail(CSE_EINVAL, __VA_ARGS__); } while (0)
+
+extern "C" {
+
+int cse_abi_version(void) { return CSE_ABI_VERSION; }
+int cse_dtype(void) { return CSE_REAL_BITS; }
+const char* cse_last_error(void) { return g_err; }
+int cse_bins_padded(int n_fft) { return cse_nbp(n_fft); }
+int cse_num_frames(int length, int hop) { return hop > 0 ? 1 + length / hop : 0; }
+
+// ------------------------------------------------------------------ tables
+size_t cse_tables_bytes(void) { return sizeof(CseTables); }
+
+static CseTables* host_tables() {
+    static CseTables* t = nullptr;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        t = new CseTables;
+        memset(t, 0, sizeof(CseTables));
+        const double PI = 3.14159265358979323846;
+        for (int k = 0; k < CSE_TW_N / 2; ++k) {
+            const double a = -2.0 * PI * k / CSE_TW_N;
+            t->tw[k] = mk2((real)cos(a), (real)sin(a));
+        }
+        auto hann = [&](real* w, int n) { for (int i = 0; i < n; ++i) w[i] = (real)(0.5 - 0.5 * cos(2.0 * PI * i / n)); };
+        hann(t->hann256, 256); hann(t->hann512, 512); hann(t->hann1024, 1024); hann(t->hann2048, 2048);
+        // np.hanning(258)[1:-1]: 0.5 - 0.5 cos(2 pi (i+1) / 257)
+        for (int i = 0; i < 256; ++i) t->stoi_win[i] = (real)(0.5 - 0.5 * cos(2.0 * PI * (i + 1) / 257.0));
+        cse_fill_resampler(t);
+    });
+    return t;
+}
+
+int cse_tables_init(void* tables, void* stream) {
+    CSE_REQUIRE(tables != nullptr, "tables is NULL");
+    cudaError_t e = cudaMemcpyAsync(tables, host_tables(), sizeof(CseTables), cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(CSE_ECUDA, "tables copy: %s", cudaGetErrorString(e));
+    return CSE_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ K1 STFT + PSD
+template <int LOG2N, int F>
+static int launch_stft(const CseTables* T, const real* wav, const real* minus, int U, int L, int hop, int nf,
+                       real floor_, real2* Y, real* P, void* stream) {
+    constexpr int M = (1 << LOG2N) / 2;
+    const size_t smem = (size_t)F * CSE_FFT_STRIDE(M) * sizeof(real2);
+    auto kfn = stft_psd_kernel<LOG2N, F>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 grid((nf + F - 1) / F, U);
+    CSE_LAUNCH(kfn, grid, 256, smem, stream, T, wav, minus, L, hop, nf, floor_, Y, P);
+    return check_launch("stft_psd_kernel");
+}
+
+extern "C" int cse_stft_psd(const void* tables, const void* wav, const void* minus, int n_utts, int length, int n_fft,
+                 int hop, double psd_floor, void* Y, void* P, void* stream) {
+    CSE_REQUIRE(tables && wav, "tables/wav is NULL");
+    CSE_REQUIRE(valid_nfft(n_fft), "n_fft %d not in {256,512,1024,2048}", n_fft);
+    CSE_REQUIRE(hop > 0 && hop <= n_fft / 2 && hop % 2 == 0, "hop %d must be even and <= n_fft/2", hop);
+    CSE_REQUIRE(n_utts > 0 && length > n_fft / 2, "need n_utts > 0 and length > n_fft/2 (reflect padding)");
+    const int nf = cse_num_frames(length, hop);
+    const CseTables* T = (const CseTables*)tables;
+    const real* w = (const real*)wav;
+    const real* m = (const real*)minus;
+    switch (n_fft) {
+        case 256: return launch_stft<8, 8>(T, w, m, n_utts, length, hop, nf, (real)psd_floor, (real2*)Y, (real*)P, stream);
+        case 512: return launch_stft<9, 8>(T, w, m, n_utts, length, hop, nf, (real)psd_floor, (real2*)Y, (real*)P, stream);
+        case 1024: return launch_stft<10, 8>(T, w, m, n_utts, length, hop, nf, (real)psd_floor, (real2*)Y, (real*)P, stream);
+        default: return launch_stft<11, 4>(T, w, m, n_utts, length, hop, nf, (real)psd_floor, (real2*)Y, (real*)P, stream);
+    }
+}
+
+// ------------------------------------------------------------------ K3+K4 gain + ISTFT
+template <int ALG, int LOG2N, int F>
+static int launch_enhance(const EnhanceArgs& a, int n_items, void* stream) {
+    constexpr int NFFT = 1 << LOG2N, M = NFFT / 2;
+    const int W = NFFT + (F - 1) * a.hop;
+    const size_t smem = (size_t)F * (CSE_FFT_STRIDE(M) + 2) * sizeof(real2) + (size_t)(2 * W + 8) * sizeof(real);
+    auto kfn = enhance_kernel<ALG, LOG2N, F>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    CSE_LAUNCH(kfn, n_items, M, smem, stream, a);
+    return check_launch("enhance_kernel");
+}
+template <int ALG>
+static int dispatch_enhance(const EnhanceArgs& a, int n_fft, int n_items, void* stream) {
+    switch (n_fft) {
+        case 256: return launch_enhance<ALG, 8, 4>(a, n_items, stream);
+        case 512: return launch_enhance<ALG, 9, 4>(a, n_items, stream);
+        case 1024: return launch_enhance<ALG, 10, 4>(a, n_items, stream);
+        default: return launch_enhance<ALG, 11, 2>(a, n_items, stream);
+    }
+}
+static real alg_eps(int algorithm) { return algorithm == CSE_ALG_MMSE ? R(1e-12) : R(1e-10); }
+
+// items [item0, item0 + n_items) of the utterance-major (utt, param) product
+static int enhance_items(const void* tables, int algorithm, const void* Y, const void* N, int noise_tv, int length,
+                         int n_fft, int hop, const cse_params* params, int n_params, int item0, int n_items,
+                         void* out, void* stream) {
+    EnhanceArgs a;
+    a.T = (const CseTables*)tables; a.Y = (const real2*)Y; a.N = (const real*)N; a.params = params;
+    a.out = (real*)out; a.noise_tv = noise_tv; a.L = length; a.hop = hop;
+    a.n_frames = cse_num_frames(length, hop); a.n_params = n_params; a.item0 = item0; a.eps = alg_eps(algorithm);
+    switch (algorithm) {
+        case CSE_ALG_SS: return dispatch_enhance<0>(a, n_fft, n_items, stream);
+        case CSE_ALG_WIENER: return dispatch_enhance<1>(a, n_fft, n_items, stream);
+        case CSE_ALG_MMSE: return dispatch_enhance<2>(a, n_fft, n_items, stream);
+        case CSE_ALG_OMLSA: return dispatch_enhance<3>(a, n_fft, n_items, stream);
+    }
+    return fail(CSE_EINVAL, "unknown algorithm %d", algorithm);
+}
+
+extern "C" int cse_enhance(const void* tables, int algorithm, const void* Y, const void* N, int noise_tv, int n_utts,
+                int length, int n_fft, int hop, const cse_params* params, int n_params, void* out, void* stream) {
+    CSE_REQUIRE(tables && Y && N && params && out, "NULL argument");
+    CSE_REQUIRE(valid_nfft(n_fft), "n_fft %d not in {256,512,1024,2048}", n_fft);
+    CSE_REQUIRE(hop > 0 && hop <= n_fft / 2 && hop % 2 == 0, "hop %d must be even and <= n_fft/2", hop);
+    CSE_REQUIRE(n_utts > 0 && n_params > 0 && length > n_fft / 2, "bad sizes");
+    CSE_REQUIRE(algorithm >= 0 && algorithm <= 3, "unknown algorithm %d", algorithm);
+    return enhance_items(tables, algorithm, Y, N, noise_tv, length, n_fft, hop, params, n_params, 0,
+                         n_utts * n_params, out, stream);
+}
+
+#include "cse_lib_noise_score.inl"

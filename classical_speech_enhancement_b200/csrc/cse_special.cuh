@@ -1,0 +1,47 @@
+// Special-function combinations of the MMSE-STSA and Log-MMSE gain rules.
+// Chebyshev coefficients come from tools/fit_special.py (scipy.special as ground truth);
+// host+device so the CPU tests can sweep them against scipy without a GPU.
+#pragma once
+#include "cse_common.cuh"
+#include "cse_special_coeffs.h"
+
+#ifdef CSE_FP64
+#define CSE_COEF(name) CSE_##name##_F64_COEFFS
+#define CSE_COEF_N(name) CSE_##name##_F64_N
+#else
+#define CSE_COEF(name) CSE_##name##_F32_COEFFS
+#define CSE_COEF_N(name) CSE_##name##_F32_N
+#endif
+
+template <int N> CSE_HD real clenshaw(const real (&c)[N], real t) {
+    real b1 = R(0), b2 = R(0);
+    const real t2 = t + t;
+#pragma unroll
+    for (int k = N - 1; k >= 1; --k) {
+        const real b0 = r_fma(t2, b1, c[k] - b2);
+        b2 = b1;
+        b1 = b0;
+    }
+    return r_fma(t, b1, c[0] - b2);
+}
+
+// M(v) = exp(-v/2) * [(1+v) I0(v/2) + v I1(v/2)],  0 <= v <= 80   (Code/mmse.py:92-96)
+CSE_HD real cse_mmse_bessel_term(real v) {
+    if (v <= R(16)) {
+        const real c[CSE_COEF_N(M_LO)] = CSE_COEF(M_LO);
+        return clenshaw(c, v * R(0.125) - R(1));
+    }
+    const real c[CSE_COEF_N(M_HI)] = CSE_COEF(M_HI);
+    return clenshaw(c, R(40) / v - R(1.5)) * r_sqrt(v);
+}
+
+// E1(v) = scipy.special.expn(1, v),  1e-12 <= v <= 80   (Code/advanced_mmse.py:103)
+CSE_HD real cse_expint_e1(real v) {
+    if (v <= R(1)) {
+        const real c[CSE_COEF_N(E_LO)] = CSE_COEF(E_LO);
+        return clenshaw(c, v + v - R(1)) - r_log(v);
+    }
+    const real c[CSE_COEF_N(E_HI)] = CSE_COEF(E_HI);
+    const real t = (R(2) / v - R(1.0125)) * R(1.0 / 0.9875);
+    return clenshaw(c, t) * r_exp(-v) / v;
+}

@@ -1,0 +1,139 @@
+/* libcse_sm100a - C ABI of the B200-native enhancement-and-scoring sweep.
+ *
+ * Drop-in boundary for the hot path of Katja39/Classical_Speech_Enhancement.  The reference
+ * has no FFI layer: its seam is the Python call `algorithm_function(noisy, sr, **param_dict)`
+ * plus the metric calls inside `optimize_parameters`
+ * (Code/speech_enhancement_comparison.py:165,177-184).  The Python package
+ * `classical_speech_enhancement_b200` re-exposes those entry points and binds the functions
+ * below with ctypes (INTEGRATION.md shows the binding a reference maintainer would add).
+ *
+ * Conventions
+ *  - plain C types only; every pointer marked [dev] is CALLER-OWNED device memory, contiguous,
+ *    16-byte aligned (PyTorch tensors' data_ptr()); the library allocates nothing;
+ *  - `real` is float in the default build and double when built with -DCSE_FP64
+ *    (cse_dtype() reports 32 or 64; same symbols either way);
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *    synchronises; results may be read after the caller synchronises the stream;
+ *  - the device is the caller's current device; no mutable global state (the FFT twiddle /
+ *    window / resampler tables are arguments the caller keeps in device memory, see
+ *    cse_tables_bytes / cse_tables_init); re-entrant across streams and devices;
+ *  - every function returns 0 (CSE_OK) or a negative CSE_E* code and never throws/exits;
+ *    cse_last_error() returns a thread-local message for the last failure.
+ *
+ * Spectrogram layout: frame-major, bin-fastest, `[utt][frame][cse_bins_padded(n_fft)]`
+ * (the transpose of librosa's (bins, frames)) so that a warp reading one frame is coalesced
+ * and the frame march of the decision-directed recursion walks memory forwards.
+ */
+#ifndef CSE_H_
+#define CSE_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSE_ABI_VERSION 1
+
+enum cse_status {
+    CSE_OK = 0,
+    CSE_EINVAL = -1,        /* bad argument (message in cse_last_error) */
+    CSE_ECUDA = -2,         /* a CUDA runtime call or launch failed */
+    CSE_EUNSUPPORTED = -3,  /* valid in the reference but outside this build's range */
+    CSE_EWORKSPACE = -4     /* caller-provided workspace too small */
+};
+
+/* Algorithms: reference table Code/speech_enhancement_comparison.py:395-401. */
+enum cse_algorithm {
+    CSE_ALG_SS = 0,      /* spectral_subtraction  Code/spectral_subtractor.py:6  */
+    CSE_ALG_WIENER = 1,  /* wiener_filter         Code/wiener_filter.py:7        */
+    CSE_ALG_MMSE = 2,    /* mmse                  Code/mmse.py:6                 */
+    CSE_ALG_OMLSA = 3    /* advanced_mmse         Code/advanced_mmse.py:7        */
+};
+
+/* One grid point.  v[] by algorithm (names are the reference's keyword arguments):
+ *   SS     : v0 alpha, v1 beta
+ *   WIENER : v0 alpha, v1 gain_floor
+ *   MMSE   : v0 alpha, v1 ksi_min, v2 gain_min, v3 gain_max, v4 noise_mu
+ *   OMLSA  : v0 alpha, v1 ksi_min, v2 gain_floor, v3 noise_mu, v4 q, v5 v_max
+ * noise_mu < 0 disables the recursive smoothing of a time-varying noise PSD (the reference
+ * applies it only when the PSD has more than one frame and noise_method != "true_noise":
+ * Code/mmse.py:48, Code/advanced_mmse.py:60). */
+typedef struct cse_params { double v[8]; } cse_params;
+
+/* One scored candidate (cse_dtype()==32 layout; the FP64 build uses double for the first two). */
+#ifdef CSE_FP64
+typedef struct cse_score_t { double stoi; double snr; int32_t lag; int32_t flags; } cse_score_t;
+#else
+typedef struct cse_score_t { float stoi; float snr; int32_t lag; int32_t flags; } cse_score_t;
+#endif
+#define CSE_FLAG_VALID 1      /* waveform finite -> candidate takes part in the selection     */
+#define CSE_FLAG_ALIGNED 2    /* a lag was estimated (reference skips it when N < 256 samples) */
+#define CSE_FLAG_SNR_INF 4    /* residual energy exactly 0: reference returns float('inf')     */
+#define CSE_FLAG_STOI_SHORT 8 /* fewer than 30 STOI frames: pystoi returns 1e-5                */
+
+int cse_abi_version(void);
+int cse_dtype(void);                    /* 32 or 64 */
+const char* cse_last_error(void);
+int cse_bins_padded(int n_fft);         /* bin stride of the spectrogram layout */
+int cse_num_frames(int length, int hop); /* 1 + length / hop (librosa center=True) */
+
+/* Constant tables (twiddles, Hann windows, STOI resampler taps, band edges).  The caller
+ * allocates cse_tables_bytes() bytes on each device once and passes the pointer to every call. */
+size_t cse_tables_bytes(void);
+int cse_tables_init(void* tables /*[dev]*/, void* stream);
+
+/* STFT + PSD.  Replaces librosa.stft(...)+abs()**2 at Code/spectral_subtractor.py:25-26,
+ * wiener_filter.py:35-37, mmse.py:29-32, advanced_mmse.py:39-40, noise_estimation.py:184-188.
+ * wav [U][L]; if `minus` is non-NULL the transform is taken of (wav - minus) and the PSD is
+ * floored at `psd_floor` (the oracle noise PSD of noise_estimation.py:128-147).
+ * Y (interleaved re,im) [U][nf][nbp] may be NULL; P [U][nf][nbp] may be NULL. */
+int cse_stft_psd(const void* tables, const void* wav, const void* minus, int n_utts, int length,
+                 int n_fft, int hop, double psd_floor, void* Y, void* P, void* stream);
+
+/* PercentileNoiseEstimator.estimate, Code/noise_estimation.py:20-56.  P [U][nf][nbp] ->
+ * N [U][nbp].  Workspace: cse_noise_workspace_bytes(). */
+size_t cse_noise_workspace_bytes(int n_utts, int n_frames, int n_fft);
+int cse_noise_percentile(const void* P, int n_utts, int n_frames, int n_fft, double percentile,
+                         double eps, void* N, void* workspace, size_t workspace_bytes, void* stream);
+
+/* MinTrackingNoiseEstimator.estimate, Code/noise_estimation.py:64-99.  P -> N [U][nf][nbp]. */
+int cse_noise_mintrack(const void* P, int n_utts, int n_frames, int n_fft, double eps, void* N,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* Gain + ISTFT for n_utts x n_params candidates (utterance-major): out[(u*n_params+c)][L].
+ * noise_tv: 0 -> N is [U][nbp] (static), 1 -> N is [U][nf][nbp] (time-varying).
+ * eps: the algorithm's epsilon (1e-10; 1e-12 for MMSE, Code/mmse.py:17).
+ * Replaces the body of the four reference entry points after their STFT / noise_estimation
+ * calls, including librosa.istft(..., length=L). */
+int cse_enhance(const void* tables, int algorithm, const void* Y, const void* N, int noise_tv,
+                int n_utts, int length, int n_fft, int hop, const cse_params* params /*[dev]*/,
+                int n_params, void* out, void* stream);
+
+/* Clean-side scoring caches (alignment spectra, STOI VAD mask / band envelopes / segment
+ * statistics, signal energy), one record of cse_clean_cache_bytes() per utterance. */
+size_t cse_clean_cache_bytes(int length, int sr);
+size_t cse_clean_workspace_bytes(int n_utts, int length, int sr);
+int cse_prepare_clean(const void* tables, const void* clean, int n_utts, int length, int sr,
+                      void* cache, void* workspace, size_t workspace_bytes, void* stream);
+
+/* finalize_enhanced + calculate_stoi + calculate_snr for n_utts x per_utt waveforms
+ * (Code/speech_enhancement_comparison.py:171-184, evaluation_metrics.py:30-58).
+ * finalize=0 scores the waveform as is (the baseline row, :116-118). */
+size_t cse_score_workspace_bytes(int n_items, int length, int sr);
+int cse_score(const void* tables, const void* wav, int n_utts, int per_utt, int length, int sr,
+              const void* clean, const void* cache, int finalize, cse_score_t* scores,
+              void* workspace, size_t workspace_bytes, void* stream);
+
+/* The batched sweep: cse_enhance + cse_score in chunks of `chunk_items` candidates whose
+ * waveforms live in the workspace (sized by cse_sweep_workspace_bytes).  scores [U*n_params]. */
+size_t cse_sweep_workspace_bytes(int chunk_items, int length, int sr);
+int cse_sweep(const void* tables, int algorithm, const void* Y, const void* N, int noise_tv,
+              int n_utts, int length, int n_fft, int hop, const cse_params* params, int n_params,
+              int sr, const void* clean, const void* cache, cse_score_t* scores,
+              int chunk_items, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSE_H_ */
