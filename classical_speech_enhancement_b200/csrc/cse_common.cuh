@@ -63,6 +63,7 @@ CSE_HD real r_fma(real a, real b, real c) { return fmaf(a, b, c); }
 // that only through np.nan_to_num, which the gain kernels restate explicitly.
 CSE_HD real r_clip(real x, real lo, real hi) { return r_min(r_max(x, lo), hi); }
 CSE_HD bool r_finite(real x) { return (x - x) == R(0); }
+CSE_HD real cse_inf() { return (real)INFINITY; }
 
 // ---------------------------------------------------------------- geometry helpers
 static inline int cse_ilog2(int n) { int l = 0; while ((1 << l) < n) ++l; return l; }
@@ -72,15 +73,15 @@ CSE_HD int cse_nbp(int n_fft) { return ((n_fft / 2 + 1) + 7) & ~7; }   // bins p
 // One blob in device memory, filled by cse_tables_init.  Offsets in units of `real`.
 #define CSE_TW_N 8192                 // twiddle table: W_8192^k = exp(-2*pi*i*k/8192), k < 4096
 #define CSE_MAX_NFFT 2048
-#define CSE_RS_TAPS 581               // STOI 16k->10k resampler (pystoi resample_oct)
-#define CSE_RS_PHASES 5
-#define CSE_RS_PHASE_TAPS 120         // 117 taps per output phase, padded to 8 x 15
+#define CSE_RS_TAPS 581               // STOI 16k->10k resampler (pystoi resample_oct), 5 phases
+#define CSE_RS_ROWS 136               // tile rows jj = (j - 8a) + 64 that can reach the 5 outputs 5a+p
 struct CseTables {
     real2 tw[CSE_TW_N / 2];
     real hann256[256], hann512[512], hann1024[1024], hann2048[2048];   // periodic Hann (librosa)
     real stoi_win[256];                                                 // np.hanning(258)[1:-1]
-    real rs[CSE_RS_PHASES][CSE_RS_PHASE_TAPS];                          // polyphase taps, see k_score
-    int rs_i0[CSE_RS_PHASES + 3];                                       // first input offset per phase
+    real rs[CSE_RS_ROWS][8];          // rs[jj][p] = h5[8p + 610 - 5jj] (0 outside the filter), p < 5
+    double rs_d[CSE_RS_ROWS][8];      // same in double for the clean-side VAD decision
+    int stoi_edges[16];               // third-octave band edges as FFT-bin indices [lo, hi)
 };
 CSE_D const real* cse_hann(const CseTables* T, int n_fft) {
     return n_fft == 256 ? T->hann256 : n_fft == 512 ? T->hann512 : n_fft == 1024 ? T->hann1024 : T->hann2048;

@@ -1,3 +1,501 @@
+// K5: per-candidate post-processing and scoring on the device.
+//
+// Restates, for sr = 16 kHz:
+//   align_to_reference   Code/speech_enhancement_comparison.py:38-69   (align_kernel)
+//   finalize_enhanced    Code/speech_enhancement_comparison.py:92-106,175 (lag shift, length
+//                        match, finite check, clip - applied on the fly by xhat())
+//   calculate_stoi       Code/evaluation_metrics.py:30-36 -> pystoi.stoi(extended=False)
+//   calculate_snr        Code/evaluation_metrics.py:39-58
+//
+// Alignment: the reference takes the argmax over |lag| <= 1600 of a 32 000-sample full
+// cross-correlation.  Only 3201 lags are needed, so the signal is cut into blocks of
+// B = 8192 - 2*1600 samples; two blocks are packed as real/imaginary parts of one 8192-point
+// complex FFT, multiplied with the cached spectrum of the matching (2*1600 longer) clean blocks
+// packed the same way, accumulated over block pairs in registers and inverse-transformed once:
+//   Re IFFT( sum_pairs Q_pair * conj(Z_pair) )[k + 1600] = sum_n clean0[n + k] * sig[n].
+// The forward transforms are DIF (bit-reversed output), the inverse is DIT (bit-reversed
+// input), so no reordering pass exists and the cached clean spectra are simply stored in DIF
+// order.  Mean removal of the candidate is applied afterwards (correlation is linear).
+//
+// STOI: polyphase 16k->10k resampling through a de-interleaved shared-memory tile, frames
+// gathered through the clean signal's VAD list (cached per utterance), 512-point real FFTs as
+// batched 256-point complex DIF FFTs, third-octave band energies, and the 30-frame segment
+// correlation against cached clean-side statistics.
 #pragma once
-#include "cse_common.cuh"
-static void cse_fill_resampler(CseTables* t) { (void)t; }
+#include "cse_fft.cuh"
+
+#define CSE_SR 16000
+#define CSE_CORR_LOG2P 13
+#define CSE_CORR_P (1 << CSE_CORR_LOG2P)
+#define CSE_MAXLAG 1600
+#define CSE_CORR_B (CSE_CORR_P - 2 * CSE_MAXLAG)
+#define CSE_CORR_SECONDS 2
+#define CSE_NBANDS 15
+#define CSE_NSEG 30
+#define CSE_STOI_T 8                   // STOI frames transformed per batch
+#define CSE_STOI_K0 7                  // first / one-past-last FFT bin used by the bands
+#define CSE_STOI_K1 219
+#define CSE_RS_A 256                   // resampler tile: input groups of 8 samples per pass
+#define CSE_RS_GROWS CSE_RS_ROWS
+
+struct CleanHeader {
+    int K;              // frames kept by the VAD
+    int J;              // number of 30-frame segments (0 -> pystoi returns 1e-5)
+    int aligned;        // correlation window >= 256 samples
+    int reserved;
+    double energy;      // sum(clean^2)
+    double ref_mean;    // mean(clean[:Nc])
+    double pad[4];
+};
+
+struct ScoreGeom {
+    int L, Nc, maxlag, nblocks, npairs, n10, nfr, nfrm, jmax;
+    size_t off_kept, off_xtob, off_seg, off_rsum, off_q, bytes;
+};
+
+static inline ScoreGeom score_geom(int L) {
+    ScoreGeom g;
+    g.L = L;
+    g.Nc = L < CSE_CORR_SECONDS * CSE_SR ? L : CSE_CORR_SECONDS * CSE_SR;
+    g.maxlag = g.Nc - 1 < CSE_MAXLAG ? g.Nc - 1 : CSE_MAXLAG;
+    g.nblocks = (g.Nc + CSE_CORR_B - 1) / CSE_CORR_B;
+    g.npairs = (g.nblocks + 1) / 2;
+    g.n10 = (5 * L + 7) / 8;
+    g.nfr = g.n10 > 256 ? (g.n10 - 256 + 127) / 128 : 0;
+    g.nfrm = g.nfr > 1 ? g.nfr - 1 : 0;
+    g.jmax = g.nfrm >= CSE_NSEG ? g.nfrm - CSE_NSEG + 1 : 0;
+    auto up = [](size_t x) { return (x + 63) & ~(size_t)63; };
+    size_t o = up(sizeof(CleanHeader));
+    g.off_kept = o; o = up(o + sizeof(int) * (size_t)(g.nfr + 1));
+    g.off_xtob = o; o = up(o + sizeof(real) * (size_t)CSE_NBANDS * (g.nfrm + 1));
+    g.off_seg = o; o = up(o + sizeof(real) * (size_t)3 * CSE_NBANDS * (g.jmax + 1));
+    g.off_rsum = o; o = up(o + sizeof(real) * (size_t)(2 * CSE_MAXLAG + 1));
+    g.off_q = o; o = up(o + sizeof(real2) * (size_t)g.npairs * CSE_CORR_P);
+    g.bytes = o;
+    return g;
+}
+
+// ---------------------------------------------------------------- resampler taps (host)
+static double cse_i0_series(double x) {          // modified Bessel I0 for the Kaiser window
+    double s = 1.0, term = 1.0;
+    const double q = 0.25 * x * x;
+    for (int k = 1; k < 64; ++k) { term *= q / ((double)k * k); s += term; if (term < 1e-20 * s) break; }
+    return s;
+}
+// pystoi 0.4.1 utils.resample_oct(x, 10000, 16000): h = kaiser(581, beta) * 2*5*fc*sinc(2 fc t),
+// fc = 1/16, beta = 0.1102 (60 - 8.7); scipy.resample_poly(x, 5, 8, window=h/sum(h)) multiplies by
+// up=5 and centres it: y[m] = sum_j x[j] h5[8m + 290 - 5j].  Tile row jj = i + 64 (i = j - 8a).
+static void cse_fill_resampler(CseTables* t) {
+    const double PI = 3.14159265358979323846;
+    const int half = 290, n = 2 * half + 1;
+    const double beta = 0.1102 * (60.0 - 8.7), fc = 1.0 / 16.0;
+    static double h[581];
+    double sum = 0.0;
+    for (int i = 0; i < n; ++i) {
+        const double tt = i - half;
+        const double xs = 2.0 * fc * tt;
+        const double sinc = tt == 0 ? 1.0 : sin(PI * xs) / (PI * xs);
+        const double r = 2.0 * i / (n - 1) - 1.0;
+        const double kaiser = cse_i0_series(beta * sqrt(1.0 - r * r)) / cse_i0_series(beta);
+        h[i] = kaiser * 2.0 * 5.0 * fc * sinc;
+        sum += h[i];
+    }
+    const int edges[16] = {7, 9, 11, 14, 17, 22, 27, 34, 43, 55, 69, 87, 109, 138, 174, 219};
+    for (int i = 0; i < 16; ++i) t->stoi_edges[i] = edges[i];
+    for (int jj = 0; jj < CSE_RS_GROWS; ++jj)
+        for (int p = 0; p < 8; ++p) {
+            const int idx = 8 * p + 610 - 5 * jj;
+            const double v = (p < 5 && idx >= 0 && idx <= 580) ? 5.0 * h[idx] / sum : 0.0;
+            t->rs[jj][p] = (real)v;
+            t->rs_d[jj][p] = v;
+        }
+}
+
+// ---------------------------------------------------------------- finalize on the fly
+// enhanced -> align shift -> match_length -> clip(-1, 1)  (speech_enhancement_comparison.py:62-67,29-36,105)
+CSE_D real xraw(const real* __restrict__ sig, int i, int lag, int L) {
+    const int j = i - lag;
+    return (j < 0 || j >= L || i < 0 || i >= L) ? R(0) : sig[j];
+}
+CSE_D real xhat(const real* __restrict__ sig, int i, int lag, int L, bool finalize) {
+    const real v = xraw(sig, i, lag, L);
+    return finalize ? r_clip(v, R(-1), R(1)) : v;
+}
+
+struct ScoreArgs {
+    const CseTables* T;
+    const real* wav;        // [n_items][L] candidates (or the clean signals in the prepare pass)
+    const real* clean;      // [U][L]
+    unsigned char* cache;   // [U] records of geom.bytes
+    cse_score_t* scores;    // [n_items]
+    real* y10;              // workspace [n_items][n10]
+    int* lagflags;          // workspace [n_items][2]
+    int per_utt, finalize, item0;   // block b scores global item item0 + b; wav / workspace are chunk-local
+    ScoreGeom g;
+};
+
+// ---------------------------------------------------------------- alignment
+template <bool CLEAN>
+__global__ void __launch_bounds__(512) align_kernel(ScoreArgs a) {
+    constexpr int P = CSE_CORR_P, NT = 512, PER = P / NT, M = CSE_MAXLAG, B = CSE_CORR_B;
+    CSE_DYN_SMEM(smem_raw);
+    real2* z = reinterpret_cast<real2*>(smem_raw);                              // CSE_FFT_STRIDE(P)
+    double* scratch = reinterpret_cast<double*>(z + CSE_FFT_STRIDE(P));         // 40 doubles
+    const int tid = threadIdx.x, li = blockIdx.x, item = a.item0 + li;
+    const int u = CLEAN ? item : item / a.per_utt;
+    const ScoreGeom& g = a.g;
+    const int L = g.L, Nc = g.Nc;
+    const real* __restrict__ sig = a.wav + (size_t)li * L;
+    unsigned char* rec = a.cache + (size_t)u * g.bytes;
+    CleanHeader* hdr = reinterpret_cast<CleanHeader*>(rec);
+    real2* Q = reinterpret_cast<real2*>(rec + g.off_q);
+    real* rsum = reinterpret_cast<real*>(rec + g.off_rsum);
+
+    // mean over the correlation window; a non-finite sample there makes the reference's whole
+    // correlation NaN, and np.argmax of an all-NaN array is index 0, i.e. lag = -max_lag
+    double s = 0.0, e2 = 0.0;
+    int bad = 0;
+    for (int i = tid; i < (CLEAN ? L : Nc); i += NT) {
+        const real v = sig[i];
+        if (i < Nc) { s += (double)v; if (!r_finite(v)) bad = 1; }
+        if (CLEAN) e2 += (double)v * (double)v;
+    }
+    const double total = block_sum<double>(s, scratch);
+    const double nbad = block_sum<double>((double)bad, scratch);
+    const double mean = total / (double)Nc;
+    const bool aligned = Nc >= 256 && (a.finalize || CLEAN);
+    if (CLEAN) {
+        const double en = block_sum<double>(e2, scratch);
+        if (tid == 0) { hdr->energy = en; hdr->ref_mean = mean; hdr->aligned = Nc >= 256; }
+    } else if (!aligned || nbad > 0.0) {
+        if (tid == 0) {
+            a.lagflags[2 * li] = aligned ? -g.maxlag : 0;
+            a.lagflags[2 * li + 1] = aligned ? (CSE_FLAG_VALID | CSE_FLAG_ALIGNED) : CSE_FLAG_VALID;
+        }
+        return;
+    }
+    if (CLEAN && Nc < 256) return;
+
+    real2 acc[PER];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) acc[k] = mk2(R(0), R(0));
+    const real meanr = (real)mean;
+    for (int pair = 0; pair < g.npairs; ++pair) {
+        const int b1 = 2 * pair, b2 = b1 + 1;
+        for (int idx = tid; idx < P; idx += NT) {
+            real re, im;
+            if (CLEAN) {        // clean blocks, 2*M samples longer, zero outside [0, Nc)
+                const int n1 = b1 * B - M + idx, n2 = b2 * B - M + idx;
+                re = (n1 >= 0 && n1 < Nc) ? sig[n1] - meanr : R(0);
+                im = (b2 < g.nblocks && n2 >= 0 && n2 < Nc) ? sig[n2] - meanr : R(0);
+            } else {
+                const int n1 = b1 * B + idx, n2 = b2 * B + idx;
+                re = (idx < B && n1 < Nc) ? sig[n1] : R(0);
+                im = (idx < B && b2 < g.nblocks && n2 < Nc) ? sig[n2] : R(0);
+            }
+            z[SIDX(idx)] = mk2(re, im);
+        }
+        __syncthreads();
+        fft_dif<CSE_CORR_LOG2P, false>(z, 1, 0, a.T->tw, tid, NT);
+        if (CLEAN) {
+            for (int idx = tid; idx < P; idx += NT) Q[(size_t)pair * P + idx] = z[SIDX(idx)];
+        } else {
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                const int idx = tid + k * NT;
+                const real2 q = Q[(size_t)pair * P + idx];
+                const real2 c = cmulc(q, z[SIDX(idx)]);
+                acc[k] = cadd(acc[k], c);
+            }
+        }
+        __syncthreads();
+    }
+    if (CLEAN) {
+        // rsum[k + M] = sum of clean0[m] over the m that lag k overlaps with (for the mean correction)
+        double t0 = 0.0;
+        for (int i = tid; i < Nc; i += NT) t0 += (double)(sig[i] - meanr);
+        const double tot0 = block_sum<double>(t0, scratch);
+        for (int kk = tid; kk <= 2 * M; kk += NT) {
+            const int k = kk - M;
+            double part = 0.0;
+            if (k >= 0) { for (int m = 0; m < k && m < Nc; ++m) part += (double)(sig[m] - meanr); }
+            else { for (int m = Nc + k < 0 ? 0 : Nc + k; m < Nc; ++m) part += (double)(sig[m] - meanr); }
+            rsum[kk] = (real)(tot0 - part);
+        }
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < PER; ++k) z[SIDX(tid + k * NT)] = acc[k];
+    __syncthreads();
+    fft_dit<CSE_CORR_LOG2P, true>(z, 1, 0, a.T->tw, tid, NT);
+    // first maximum over k = -maxlag .. maxlag
+    const real invP = R(1) / (real)P;
+    real best = -cse_inf();
+    int bestk = 0x7fffffff;
+    for (int k = -g.maxlag + tid; k <= g.maxlag; k += NT) {
+        const real c = z[SIDX(k + M)].x * invP - meanr * rsum[k + M];
+        if (c > best) { best = c; bestk = k; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const real ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, bestk, o);
+        if (ob > best || (ob == best && ok < bestk)) { best = ob; bestk = ok; }
+    }
+    real* sb = reinterpret_cast<real*>(scratch);
+    int* sk = reinterpret_cast<int*>(scratch + 20);
+    __syncthreads();
+    if ((tid & 31) == 0) { sb[tid >> 5] = best; sk[tid >> 5] = bestk; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < NT / 32; ++w)
+            if (sb[w] > best || (sb[w] == best && sk[w] < bestk)) { best = sb[w]; bestk = sk[w]; }
+        if (bestk == 0x7fffffff) bestk = -g.maxlag;      // all-NaN: np.argmax returns index 0
+        a.lagflags[2 * li] = bestk;
+        a.lagflags[2 * li + 1] = CSE_FLAG_VALID | CSE_FLAG_ALIGNED;
+    }
+}
+
+// ---------------------------------------------------------------- resampler
+// One pass: outputs y10[5a + p], a in [a0, a0 + A), from the de-interleaved tile xs[c][ap]
+// (c = sample index mod 8, AP = A + 17 columns).  TA = accumulator type.
+template <class TA, class TG, class TO>
+CSE_D void resample_pass(const real* __restrict__ sig, int L, int lag, bool finalize, const TG* __restrict__ G /*[136][8]*/,
+                         TA* xs, int a0, TO* __restrict__ y10, int n10, int tid, int nth) {
+    constexpr int A = CSE_RS_A, AP = A + 17;
+    const int j0 = 8 * a0 - 64;
+    for (int jj = tid; jj < 8 * AP; jj += nth) xs[(jj & 7) * AP + (jj >> 3)] = (TA)xhat(sig, j0 + jj, lag, L, finalize);
+    __syncthreads();
+    for (int al = tid; al < A; al += nth) {
+        const int a = a0 + al;
+        if (5 * a < n10) {
+            TA acc[5] = {0, 0, 0, 0, 0};
+            for (int o = 0; o < 17; ++o) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const TA x = xs[c * AP + al + o];
+                    const TG* g = G + (size_t)(8 * o + c) * 8;
+#pragma unroll
+                    for (int p = 0; p < 5; ++p) acc[p] += x * (TA)g[p];
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 5; ++p) if (5 * a + p < n10) y10[5 * a + p] = (TO)acc[p];
+        }
+    }
+    __syncthreads();
+}
+
+// clean-side resampling + VAD (pystoi remove_silent_frames, mask from the clean signal only)
+// grid U, block 256; y10 (real) goes to the workspace for clean_stoi.
+__global__ void __launch_bounds__(256) clean_vad_kernel(ScoreArgs a, double* __restrict__ y10d, double* __restrict__ energies) {
+    CSE_DYN_SMEM(smem_raw);
+    double* xs = reinterpret_cast<double*>(smem_raw);             // 8 * (A + 17)
+    double* scratch = xs + 8 * (CSE_RS_A + 17);                   // 40
+    const int tid = threadIdx.x, u = blockIdx.x;
+    const ScoreGeom& g = a.g;
+    const real* sig = a.wav + (size_t)u * g.L;
+    double* yd = y10d + (size_t)u * g.n10;
+    unsigned char* rec = a.cache + (size_t)u * g.bytes;
+    CleanHeader* hdr = reinterpret_cast<CleanHeader*>(rec);
+    int* kept = reinterpret_cast<int*>(rec + g.off_kept);
+    const int na = (g.n10 + 4) / 5;
+    for (int a0 = 0; a0 < na; a0 += CSE_RS_A)
+        resample_pass<double, double, double>(sig, g.L, 0, false, &a.T->rs_d[0][0], xs, a0, yd, g.n10, tid, 256);
+    __threadfence_block();
+    __syncthreads();
+    // frame energies in dB: 20 log10(||w * frame|| + EPS)
+    const double EPS = 2.220446049250313e-16;
+    double* en = energies + (size_t)u * (g.nfr + 1);
+    double emax = -1e300;
+    for (int f = tid; f < g.nfr; f += 256) {
+        double e = 0.0;
+        for (int n = 0; n < 256; ++n) { const double v = (double)a.T->stoi_win[n] * yd[128 * f + n]; e += v * v; }
+        e = 20.0 * log10(sqrt(e) + EPS);
+        en[f] = e;
+        emax = e > emax ? e : emax;
+    }
+    // block max
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, emax, o); emax = t > emax ? t : emax; }
+    __syncthreads();
+    if ((tid & 31) == 0) scratch[tid >> 5] = emax;
+    __syncthreads();
+    emax = scratch[0];
+    for (int w = 1; w < 8; ++w) emax = scratch[w] > emax ? scratch[w] : emax;
+    __syncthreads();
+    // mask = (max - 40 dB - e) < 0, then ordered compaction into the kept-frame list
+    if (tid == 0) {
+        int K = 0;
+        for (int f = 0; f < g.nfr; ++f) if ((emax - 40.0 - en[f]) < 0.0) kept[K++] = f;
+        hdr->K = K;
+        hdr->J = (K - 1 >= CSE_NSEG) ? (K - 1) - CSE_NSEG + 1 : 0;
+    }
+}
+
+// ---------------------------------------------------------------- STOI + SNR
+// MODE 0: score a candidate.  MODE 1: clean-side pass (band envelopes + segment statistics into
+// the cache; y10 already in the workspace as double).
+template <int MODE>
+__global__ void __launch_bounds__(256) stoi_kernel(ScoreArgs a, const double* __restrict__ y10d) {
+    constexpr int T = CSE_STOI_T, BST = CSE_FFT_STRIDE(256), NK = CSE_STOI_K1 - CSE_STOI_K0, NT = 256;
+    CSE_DYN_SMEM(smem_raw);
+    const ScoreGeom& g = a.g;
+    const int tid = threadIdx.x, li = blockIdx.x, item = a.item0 + li;
+    const int u = MODE == 1 ? item : item / a.per_utt;
+    unsigned char* rec = a.cache + (size_t)u * g.bytes;
+    const CleanHeader* hdr = reinterpret_cast<const CleanHeader*>(rec);
+    const int* __restrict__ kept = reinterpret_cast<const int*>(rec + g.off_kept);
+    real* xtob_c = reinterpret_cast<real*>(rec + g.off_xtob);
+    real* seg_c = reinterpret_cast<real*>(rec + g.off_seg);
+    const int K = hdr->K, Kf = K > 0 ? K - 1 : 0, J = hdr->J;
+
+    double* scratch = reinterpret_cast<double*>(smem_raw);                    // 40 doubles
+    real* gtab = reinterpret_cast<real*>(scratch + 40);                       // 136 * 8
+    real2* fbuf = reinterpret_cast<real2*>(gtab + CSE_RS_GROWS * 8);          // T * BST (aliases the resampler tile)
+    real* pw = reinterpret_cast<real*>(fbuf + T * BST);                       // T * NK
+    real* ytob = pw + T * NK;                                                 // 15 * Kf
+    real* xtob = ytob + CSE_NBANDS * (g.nfrm + 1);                            // 15 * Kf (MODE 0)
+    real* xs = reinterpret_cast<real*>(fbuf);
+
+    const real* __restrict__ sig = a.wav + (size_t)li * g.L;
+    real* y10 = a.y10 + (size_t)li * g.n10;
+    int lag = 0, flags = CSE_FLAG_VALID;
+    const bool fin = MODE == 0 && a.finalize;
+    if (MODE == 0) {
+        lag = a.lagflags[2 * li];
+        flags = a.lagflags[2 * li + 1];
+        // global SNR: 10 log10( sum c^2 / (sum (c - x)^2 + 1e-10) ), and the finite check of
+        // finalize_enhanced over the samples that survive the shift (:102-103)
+        const real* __restrict__ cl = a.clean + (size_t)u * g.L;
+        real pn = R(0);
+        int bad = 0;
+        for (int i = tid; i < g.L; i += NT) {
+            const real raw = xraw(sig, i, lag, g.L);
+            if (!r_finite(raw)) bad = 1;
+            const real d = cl[i] - (fin ? r_clip(raw, R(-1), R(1)) : raw);
+            pn = r_fma(d, d, pn);
+        }
+        const double nbad = block_sum<double>((double)bad, scratch);
+        if (nbad > 0.0) {
+            if (tid == 0) { cse_score_t sc; sc.stoi = R(0); sc.snr = R(0); sc.lag = lag; sc.flags = 0; a.scores[item] = sc; }
+            return;
+        }
+        const double pnoise = block_sum<double>((double)pn, scratch);
+        for (int i = tid; i < CSE_RS_GROWS * 8; i += NT) gtab[i] = (&a.T->rs[0][0])[i];
+        for (int i = tid; i < CSE_NBANDS * Kf; i += NT) xtob[i] = xtob_c[i];
+        __syncthreads();
+        const int na = (g.n10 + 4) / 5;
+        for (int a0 = 0; a0 < na; a0 += CSE_RS_A)
+            resample_pass<real, real, real>(sig, g.L, lag, fin, gtab, xs, a0, y10, g.n10, tid, NT);
+        __threadfence_block();
+        __syncthreads();
+        if (tid == 0) {
+            real snr;
+            if (pnoise == 0.0) { snr = cse_inf(); flags |= CSE_FLAG_SNR_INF; }
+            else snr = (real)(10.0 * log10(hdr->energy / (pnoise + 1e-10)));
+            a.scores[item].snr = snr;
+            a.scores[item].lag = lag;
+        }
+    }
+    if (Kf < CSE_NSEG) {
+        if (MODE == 0 && tid == 0) { a.scores[item].stoi = R(1e-5); a.scores[item].flags = flags | CSE_FLAG_STOI_SHORT; }
+        return;
+    }
+    const real* __restrict__ w = a.T->stoi_win;
+    const int* __restrict__ edges = a.T->stoi_edges;
+    const double* ydu = MODE == 1 ? y10d + (size_t)u * g.n10 : nullptr;
+    auto ysamp = [&](int i) -> real { return MODE == 1 ? (real)ydu[i] : y10[i]; };
+
+    for (int m0 = 0; m0 < Kf; m0 += T) {
+        // frames of the silence-removed signal: sample n of frame m is
+        //   w[n] * (F_m[n] + F_{m-1}[n+128])  (n < 128),  w[n] * (F_{m+1}[n-128] + F_m[n])  (n >= 128),
+        // F_j[n] = w[n] * y10[128 kept[j] + n]
+        for (int idx = tid; idx < T * 256; idx += NT) {
+            const int f = idx >> 8, mm = idx & 255, m = m0 + f;
+            real2 v = mk2(R(0), R(0));
+            if (mm < 128 && m < Kf) {
+                const int kc = 128 * kept[m];
+                real s[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int n = 2 * mm + e;
+                    real acc = w[n] * ysamp(kc + n);
+                    if (n < 128) { if (m > 0) acc += w[n + 128] * ysamp(128 * kept[m - 1] + n + 128); }
+                    else acc += w[n - 128] * ysamp(128 * kept[m + 1] + n - 128);
+                    s[e] = w[n] * acc;
+                }
+                v = mk2(s[0], s[1]);
+            }
+            fbuf[f * BST + SIDX(mm)] = v;
+        }
+        __syncthreads();
+        fft_dif<8, false>(fbuf, T, BST, a.T->tw, tid, NT);
+        for (int idx = tid; idx < T * NK; idx += NT) {
+            const int f = idx / NK, k = CSE_STOI_K0 + (idx - f * NK);
+            const real2* zf = fbuf + f * BST;
+            const real2 z0 = zf[SIDX(brev_n(k, 8))], z1 = zf[SIDX(brev_n(256 - k, 8))];
+            const real2 E = mk2(R(0.5) * (z0.x + z1.x), R(0.5) * (z0.y - z1.y));
+            const real2 O = mk2(R(0.5) * (z0.y + z1.y), R(-0.5) * (z0.x - z1.x));
+            const real2 X = cadd(E, cmul(O, tw_load(a.T->tw, k * (CSE_TW_N / 512))));
+            pw[idx] = X.x * X.x + X.y * X.y;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < T * CSE_NBANDS; idx += NT) {
+            const int f = idx / CSE_NBANDS, b = idx - f * CSE_NBANDS, m = m0 + f;
+            if (m < Kf) {
+                real sacc = R(0);
+                for (int k = edges[b]; k < edges[b + 1]; ++k) sacc += pw[f * NK + k - CSE_STOI_K0];
+                ytob[b * Kf + m] = r_sqrt(sacc);
+            }
+        }
+        __syncthreads();
+    }
+
+    const real EPS = R(2.220446049250313e-16);
+    if (MODE == 1) {
+        // clean side: envelopes + per (segment, band) norm, mean, 1/(centred norm + EPS)
+        for (int i = tid; i < CSE_NBANDS * Kf; i += NT) xtob_c[i] = ytob[i];
+        for (int idx = tid; idx < J * CSE_NBANDS; idx += NT) {
+            const int j = idx / CSE_NBANDS, b = idx - j * CSE_NBANDS;
+            const real* x = ytob + b * Kf + j;
+            real s1 = R(0), s2 = R(0);
+            for (int n = 0; n < CSE_NSEG; ++n) { s1 += x[n]; s2 = r_fma(x[n], x[n], s2); }
+            const real mean = s1 / R(CSE_NSEG);
+            real c2 = R(0);
+            for (int n = 0; n < CSE_NSEG; ++n) { const real d = x[n] - mean; c2 = r_fma(d, d, c2); }
+            seg_c[(size_t)0 * J * CSE_NBANDS + idx] = r_sqrt(s2);
+            seg_c[(size_t)1 * J * CSE_NBANDS + idx] = mean;
+            seg_c[(size_t)2 * J * CSE_NBANDS + idx] = R(1) / (r_sqrt(c2) + EPS);
+        }
+        return;
+    }
+    // d = mean over (segment, band) of corr( clip(alpha Y, (1 + 10^(15/20)) X) , X )
+    const real clipc = R(1) + R(5.623413251903491);
+    real dsum = R(0);
+    for (int idx = tid; idx < J * CSE_NBANDS; idx += NT) {
+        const int j = idx / CSE_NBANDS, b = idx - j * CSE_NBANDS;
+        const real* x = xtob + b * Kf + j;
+        const real* y = ytob + b * Kf + j;
+        const real xn = seg_c[idx], xmean = seg_c[(size_t)J * CSE_NBANDS + idx], xinv = seg_c[(size_t)2 * J * CSE_NBANDS + idx];
+        real y2 = R(0);
+        for (int n = 0; n < CSE_NSEG; ++n) y2 = r_fma(y[n], y[n], y2);
+        const real alpha = xn / (r_sqrt(y2) + EPS);
+        real s1 = R(0);
+        for (int n = 0; n < CSE_NSEG; ++n) s1 += r_min(alpha * y[n], clipc * x[n]);
+        const real ymean = s1 / R(CSE_NSEG);
+        real c2 = R(0), cx = R(0);
+        for (int n = 0; n < CSE_NSEG; ++n) {
+            const real d = r_min(alpha * y[n], clipc * x[n]) - ymean;
+            c2 = r_fma(d, d, c2);
+            cx = r_fma(d, x[n] - xmean, cx);
+        }
+        dsum += cx * xinv / (r_sqrt(c2) + EPS);
+    }
+    const double dtot = block_sum<double>((double)dsum, scratch);
+    if (tid == 0) {
+        a.scores[item].stoi = (real)(dtot / ((double)J * CSE_NBANDS));
+        a.scores[item].flags = flags;
+    }
+}
+

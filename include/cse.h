@@ -133,6 +133,11 @@ int cse_sweep(const void* tables, int algorithm, const void* Y, const void* N, i
               int sr, const void* clean, const void* cache, cse_score_t* scores,
               int chunk_items, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Host-side probe used by the tests: evaluates the special-function fits the gain kernels
+ * inline (which = 0: exp(-v/2)[(1+v)I0(v/2)+vI1(v/2)] of Code/mmse.py:92-96; 1: E1(v) of
+ * Code/advanced_mmse.py:103) at x[0..n) in the library's precision. */
+int cse_debug_special(int which, const double* x, double* y, int n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,3 +62,45 @@ class Emu:
             out = np.zeros((1, N_oracle.shape[1], nbp), dtype=self.real)
             out[0, :, :nb] = N_oracle.T
         return out
+
+    def noise_percentile(self, P, n_fft, percentile, eps):
+        U, nf, nbp = P.shape
+        N = np.zeros((U, nbp), dtype=self.real)
+        ws = np.zeros(self.lib.noise_workspace_bytes(U, nf, n_fft), dtype=np.uint8)
+        self.lib.noise_percentile(ptr(P), U, nf, n_fft, percentile, eps, ptr(N), ptr(ws), ws.nbytes, None)
+        return N
+
+    def noise_mintrack(self, P, n_fft, eps):
+        U, nf, nbp = P.shape
+        N = np.zeros((U, nf, nbp), dtype=self.real)
+        self.lib.noise_mintrack(ptr(P), U, nf, n_fft, eps, ptr(N), None, 0, None)
+        return N
+
+    def prepare_clean(self, clean):
+        clean = np.ascontiguousarray(np.atleast_2d(clean), dtype=self.real)
+        U, L = clean.shape
+        rec = self.lib.clean_cache_bytes(L, 16000)
+        cache = np.zeros(U * rec, dtype=np.uint8)
+        ws = np.zeros(self.lib.clean_workspace_bytes(U, L, 16000), dtype=np.uint8)
+        self.lib.prepare_clean(ptr(self.tables), ptr(clean), U, L, 16000, ptr(cache), ptr(ws), ws.nbytes, None)
+        return clean, cache
+
+    def score(self, wav, clean, cache, finalize=True):
+        """wav [U][C][L] -> structured scores [U][C]."""
+        wav = np.ascontiguousarray(wav, dtype=self.real)
+        U, C, L = wav.shape
+        scores = np.zeros(U * C, dtype=self.lib.score_dtype)
+        ws = np.zeros(self.lib.score_workspace_bytes(U * C, L, 16000), dtype=np.uint8)
+        self.lib.score(ptr(self.tables), ptr(wav), U, C, L, 16000, ptr(clean), ptr(cache), int(finalize),
+                       ptr(scores), ptr(ws), ws.nbytes, None)
+        return scores.reshape(U, C)
+
+    def sweep(self, alg, Y, N, L, n_fft, hop, rows, clean, cache, chunk=3):
+        U = Y.shape[0]
+        params = pack_params(rows)
+        N = np.ascontiguousarray(N, dtype=self.real)
+        scores = np.zeros(U * len(rows), dtype=self.lib.score_dtype)
+        ws = np.zeros(self.lib.sweep_workspace_bytes(chunk, L, 16000), dtype=np.uint8)
+        self.lib.sweep(ptr(self.tables), alg, ptr(Y), ptr(N), int(N.ndim == 3), U, L, n_fft, hop, ptr(params),
+                       len(rows), 16000, ptr(clean), ptr(cache), ptr(scores), chunk, ptr(ws), ws.nbytes, None)
+        return scores.reshape(U, len(rows))
