@@ -40,6 +40,8 @@ SIGNATURES = {
     "cse_score_workspace_bytes": (_sz, [_i, _i, _i]),
     "cse_score": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "cse_sweep_workspace_bytes": (_sz, [_i, _i, _i]),
+    "cse_enhance_items": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
+    "cse_score_items": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "cse_debug_special": (_i, [_i, _vp, _vp, _i]),
     "cse_sweep": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
 }

@@ -185,6 +185,27 @@ extern "C" int cse_sweep(const void* tables, int algorithm, const void* Y, const
     return CSE_OK;
 }
 
+extern "C" int cse_enhance_items(const void* tables, int algorithm, const void* Y, const void* N, int noise_tv,
+                                 int length, int n_fft, int hop, const cse_params* params, int n_params, int item0,
+                                 int n_items, void* out, void* stream) {
+    CSE_REQUIRE(tables && Y && N && params && out, "NULL argument");
+    CSE_REQUIRE(valid_nfft(n_fft), "n_fft %d not in {256,512,1024,2048}", n_fft);
+    CSE_REQUIRE(hop > 0 && hop <= n_fft / 2 && hop % 2 == 0, "hop %d must be even and <= n_fft/2", hop);
+    CSE_REQUIRE(n_params > 0 && n_items > 0 && item0 >= 0 && length > n_fft / 2, "bad sizes");
+    CSE_REQUIRE(algorithm >= 0 && algorithm <= 3, "unknown algorithm %d", algorithm);
+    return enhance_items(tables, algorithm, Y, N, noise_tv, length, n_fft, hop, params, n_params, item0, n_items, out, stream);
+}
+
+extern "C" int cse_score_items(const void* tables, const void* wav, int item0, int n_items, int per_utt, int length,
+                               int sr, const void* clean, const void* cache, int finalize, cse_score_t* scores,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    CSE_REQUIRE(tables && wav && clean && cache && scores && workspace, "NULL argument");
+    CSE_REQUIRE(n_items > 0 && item0 >= 0 && per_utt > 0 && length > 0, "bad sizes");
+    if (int rc = check_sr(sr)) return rc;
+    if (workspace_bytes < cse_score_workspace_bytes(n_items, length, sr)) return fail(CSE_EWORKSPACE, "score workspace too small");
+    return score_items(tables, wav, item0, n_items, per_utt, length, clean, cache, finalize, scores, workspace, stream);
+}
+
 // ------------------------------------------------------------------ host-side probes for tests
 // Evaluates the gain rules' special-function fits on the host (same code the kernels inline).
 extern "C" int cse_debug_special(int which, const double* x, double* y, int n) {

@@ -1,0 +1,72 @@
+"""Multi-GPU sharding of the sweep: one process per GPU, utterances split in contiguous blocks.
+
+Every (utterance, algorithm, grid point) is independent; the only coupling is the
+per-(utterance, algorithm) selection scan, so utterances are partitioned across ranks, each rank
+runs the complete grid for its block with its own caches, and ONE collective at the end gathers
+the per-point score tables for the host-side selection (``torch.distributed`` all_gather: NCCL
+over NVLink on GPUs, gloo in the CPU tests).  The reference has no distributed code at all
+(SURVEY.md section 5); this is its B200-native replacement for running ``main()`` for a day.
+"""
+import numpy as np
+
+
+def shard_bounds(n_utts, world_size):
+    """Contiguous, balanced blocks: rank r owns [b[r], b[r+1])."""
+    base, rem = divmod(n_utts, world_size)
+    b = [0]
+    for r in range(world_size):
+        b.append(b[-1] + base + (1 if r < rem else 0))
+    return b
+
+
+def local_slice(n_utts, rank, world_size):
+    b = shard_bounds(n_utts, world_size)
+    return slice(b[rank], b[rank + 1])
+
+
+def gather_scores(local, n_utts, device=None):
+    """all_gather of a structured score table [U_local, C] -> [n_utts, C] on every rank.
+
+    The table travels as raw bytes (scores are already final per point: no reduction, so the
+    N-GPU result equals the 1-GPU result bit for bit).  Blocks are padded to the largest shard so
+    that one fixed-size all_gather suffices."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    b = shard_bounds(n_utts, world)
+    assert local.shape[0] == b[rank + 1] - b[rank]
+    C = local.shape[1]
+    row_bytes = C * local.dtype.itemsize
+    max_rows = max(b[r + 1] - b[r] for r in range(world))
+    buf = np.zeros((max_rows, row_bytes), dtype=np.uint8)
+    buf[:local.shape[0]] = np.ascontiguousarray(local).view(np.uint8).reshape(local.shape[0], row_bytes)
+    send = torch.from_numpy(buf)
+    if device is not None:
+        send = send.to(device)
+    recv = torch.empty((world,) + tuple(send.shape), dtype=torch.uint8, device=send.device)
+    dist.all_gather_into_tensor(recv, send) if send.is_cuda else dist.all_gather(list(recv.unbind(0)), send)
+    recv = recv.cpu().numpy()
+    out = np.zeros((n_utts, C), dtype=local.dtype)
+    for r in range(world):
+        n = b[r + 1] - b[r]
+        out[b[r]:b[r + 1]] = recv[r, :n].reshape(-1).view(local.dtype).reshape(n, C)
+    return out
+
+
+def sweep_sharded(clean, noisy, grids=None, select=True, chunk_items=1184, device=None, engine_kwargs=None):
+    """Each rank sweeps its block of utterances; every rank returns the full gathered tables.
+    ``clean`` / ``noisy`` are the full host arrays [U, L] (each rank slices its block)."""
+    import torch.distributed as dist
+    from . import sweep as sw
+    grids = grids or sw.DEFAULT_GRIDS
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    sl = local_slice(clean.shape[0], rank, world)
+    local = sw.sweep_dataset(clean[sl], noisy[sl], grids=grids, select=False, chunk_items=chunk_items,
+                             engine_kwargs=engine_kwargs)
+    scores = {name: gather_scores(sc, clean.shape[0], device=device) for name, sc in local["scores"].items()}
+    return {"scores": scores, "points": local["points"],
+            "selection": sw.select_all(scores, local["points"]) if select else None,
+            "local_engine": local["engine"]}

@@ -1,0 +1,333 @@
+"""Batched sweep engine: the host side of the (utterance x grid-point) batch.
+
+Owns the device-resident state of one batch of equal-length utterance pairs - waveforms,
+clean-side scoring caches, one STFT per (n_fft, hop), one noise PSD per
+(n_fft, hop, method, percentile, eps) - and drives the C ABI (``include/cse.h``).  The
+reference recomputes all of that for every candidate (``Code/wiener_filter.py:35-46`` +
+``Code/noise_estimation.py:184-188``); here it is computed once and shared by the hundreds of
+candidates that differ only in gain parameters.
+
+Array storage goes through a small backend so that the same engine logic runs on CUDA tensors
+(product: :class:`TorchCudaBackend`, PyTorch is only the buffer carrier) and, in the CPU test
+suite, on numpy arrays against the thread-emulated kernels.  There is no CPU compute path in
+the product: constructing :class:`SweepEngine` without a CUDA device raises.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .grid import ALGORITHM_IDS, alg_eps, grid_points, plan
+
+SR = 16000
+
+#: runtime used when an engine is constructed without explicit lib/backend.  The product never
+#: changes it (-> libcse_sm100a.so + CUDA tensors); the CPU test-suite points it at the
+#: thread-emulated build to exercise the host logic without a GPU.
+_runtime = {"lib": None, "backend_factory": None}
+
+
+def configure_runtime(lib=None, backend_factory=None):
+    _runtime["lib"] = lib
+    _runtime["backend_factory"] = backend_factory
+
+
+class TorchCudaBackend:
+    """Device buffers as torch CUDA tensors; all work on torch's current stream."""
+
+    def __init__(self, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.CseLibraryError("no CUDA device: this path has no CPU fallback")
+        self.torch = torch
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+
+    def empty(self, shape, dtype):
+        t = self.torch
+        td = {np.float32: t.float32, np.float64: t.float64, np.uint8: t.uint8, np.int32: t.int32}[np.dtype(dtype).type]
+        return t.empty(shape, dtype=td, device=self.device)
+
+    def zeros(self, shape, dtype):
+        return self.empty(shape, dtype).zero_()
+
+    def from_host(self, arr, pinned=False):
+        t = self.torch.from_numpy(np.ascontiguousarray(arr))
+        if pinned:
+            t = t.pin_memory()
+        return t.to(self.device, non_blocking=True)
+
+    def to_host(self, buf):
+        return buf.cpu().numpy()
+
+    def ptr(self, buf):
+        return None if buf is None else ctypes.c_void_p(buf.data_ptr())
+
+    def stream(self):
+        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def synchronize(self):
+        self.torch.cuda.current_stream(self.device).synchronize()
+
+    def event(self):
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record(self.torch.cuda.current_stream(self.device))
+        return e
+
+    def view_bytes_as(self, buf, dtype):
+        return buf.cpu().numpy().view(dtype)
+
+    def slice_rows(self, buf, start, stop):
+        return buf[start:stop]
+
+
+class SweepEngine:
+    """One batch of ``U`` equal-length (clean, noisy) pairs resident on one device."""
+
+    def __init__(self, clean, noisy, sr=SR, lib=None, backend=None, chunk_items=1184, prepare_scoring=True):
+        if sr != SR:
+            raise ValueError("the sweep runs at 16 kHz (the reference resamples every pair to 16 kHz first)")
+        self.lib = lib if lib is not None else (_runtime["lib"] or _lib.load())
+        self.be = backend if backend is not None else (
+            _runtime["backend_factory"]() if _runtime["backend_factory"] else TorchCudaBackend())
+        self.real = self.lib.real
+        noisy = np.atleast_2d(np.asarray(noisy))
+        self.has_clean = clean is not None
+        clean = np.atleast_2d(np.asarray(clean)) if self.has_clean else np.zeros_like(noisy)
+        if clean.shape != noisy.shape or clean.ndim != 2:
+            raise ValueError("clean and noisy must both be [U, L]")
+        self.U, self.L = clean.shape
+        self.chunk_items = int(chunk_items)
+        be, lib_ = self.be, self.lib
+        self.tables = be.empty((lib_.tables_bytes(),), np.uint8)
+        lib_.tables_init(be.ptr(self.tables), be.stream())
+        self.clean = be.from_host(clean.astype(self.real))
+        self.noisy = be.from_host(noisy.astype(self.real))
+        self.h2d_bytes = 2 * clean.size * np.dtype(self.real).itemsize
+        self._stft = {}
+        self._noise = {}
+        self._ws = {}
+        self.launches = 0
+        if not self.has_clean or not prepare_scoring:
+            self.cache = None
+            return
+        rec = lib_.clean_cache_bytes(self.L, sr)
+        self.cache = be.zeros((self.U * rec,), np.uint8)
+        ws = self._workspace("clean", lib_.clean_workspace_bytes(self.U, self.L, sr))
+        lib_.prepare_clean(be.ptr(self.tables), be.ptr(self.clean), self.U, self.L, sr, be.ptr(self.cache),
+                           be.ptr(ws), self._ws["clean"][1], be.stream())
+        self.launches += 3
+
+    # ------------------------------------------------------------------ optional kernel timing
+    def enable_timing(self, on=True):
+        """Bracket every chunk's enhance / score launches with events on the launching stream."""
+        self._timing = [] if on else None
+
+    def _tick(self):
+        if getattr(self, "_timing", None) is None or not hasattr(self.be, "event"):
+            return None
+        return self.be.event()
+
+    def _record(self, tag, n_items, e0, e1):
+        if e0 is not None:
+            self._timing.append((tag, n_items, e0, e1))
+
+    def timing_summary(self):
+        """{tag: (items, milliseconds)} after a synchronize; events are torch CUDA events."""
+        out = {}
+        for tag, n, e0, e1 in (getattr(self, "_timing", None) or []):
+            it, ms = out.get(tag, (0, 0.0))
+            out[tag] = (it + n, ms + e0.elapsed_time(e1))
+        return out
+
+    # ------------------------------------------------------------------ caches
+    def _workspace(self, name, nbytes):
+        nbytes = max(int(nbytes), 64)
+        cur = self._ws.get(name)
+        if cur is None or cur[1] < nbytes:
+            self._ws[name] = (self.be.empty((nbytes,), np.uint8), nbytes)
+        return self._ws[name][0]
+
+    def n_frames(self, n_fft, hop):
+        return self.lib.num_frames(self.L, hop)
+
+    def stft(self, n_fft, hop):
+        """Y [U][nf][nbp] (complex as interleaved reals) of the noisy signals, cached per shape."""
+        key = (n_fft, hop)
+        if key not in self._stft:
+            nf, nbp = self.n_frames(n_fft, hop), self.lib.bins_padded(n_fft)
+            Y = self.be.empty((self.U, nf, nbp, 2), self.real)
+            self.lib.stft_psd(self.be.ptr(self.tables), self.be.ptr(self.noisy), None, self.U, self.L, n_fft, hop,
+                              0.0, self.be.ptr(Y), None, self.be.stream())
+            self.launches += 1
+            self._stft[key] = Y
+        return self._stft[key]
+
+    def _power(self, n_fft, hop):
+        nf, nbp = self.n_frames(n_fft, hop), self.lib.bins_padded(n_fft)
+        P = self.be.empty((self.U, nf, nbp), self.real)
+        self.lib.stft_psd(self.be.ptr(self.tables), self.be.ptr(self.noisy), None, self.U, self.L, n_fft, hop, 0.0,
+                          None, self.be.ptr(P), self.be.stream())
+        self.launches += 1
+        return P
+
+    def noise(self, key):
+        """Noise PSD for key = (n_fft, hop, method, percentile|None, eps) -> (buffer, time_varying)."""
+        if key in self._noise:
+            return self._noise[key]
+        n_fft, hop, method, pct, eps = key
+        be, lib_ = self.be, self.lib
+        nf, nbp = self.n_frames(n_fft, hop), lib_.bins_padded(n_fft)
+        if nf < 5 or method == "percentile":
+            # short signals: every method falls back to the 25th percentile (noise_estimation.py:194-195)
+            P = self._power(n_fft, hop)
+            N = be.zeros((self.U, nbp), self.real)
+            nbytes = lib_.noise_workspace_bytes(self.U, nf, n_fft)
+            ws = self._workspace("noise", nbytes)
+            lib_.noise_percentile(be.ptr(P), self.U, nf, n_fft, 20.0 if pct is None else pct, eps, be.ptr(N),
+                                  be.ptr(ws), nbytes, be.stream())
+            self.launches += 3
+            out = (N, False)
+        elif method == "min_tracking":
+            P = self._power(n_fft, hop)
+            N = be.zeros((self.U, nf, nbp), self.real)
+            lib_.noise_mintrack(be.ptr(P), self.U, nf, n_fft, eps, be.ptr(N), None, 0, be.stream())
+            self.launches += 1
+            out = (N, True)
+        elif method == "true_noise":
+            if not self.has_clean:
+                raise ValueError("TrueNoiseEstimator requires clean_audio and noisy_audio")
+            N = be.zeros((self.U, nf, nbp), self.real)
+            lib_.stft_psd(be.ptr(self.tables), be.ptr(self.noisy), be.ptr(self.clean), self.U, self.L, n_fft, hop,
+                          eps, None, be.ptr(N), be.stream())
+            self.launches += 1
+            out = (N, True)
+        else:
+            raise ValueError(f"Unbekannte Methode: {method}")
+        self._noise[key] = out
+        return out
+
+    def drop_caches(self):
+        self._stft.clear()
+        self._noise.clear()
+
+    # ------------------------------------------------------------------ the sweep
+    def sweep(self, alg_name, points):
+        """Scores of every grid point for every utterance.
+
+        Returns a structured array [U, len(points)] (stoi, snr, lag, flags) in the reference's
+        grid order.  Points that differ only in dead parameters are computed once and their
+        score broadcast (the reference would produce bit-identical duplicates).  ``unique`` is
+        recorded in ``self.last_unique``.
+        """
+        alg = ALGORITHM_IDS[alg_name] if isinstance(alg_name, str) else int(alg_name)
+        groups = plan(alg, points, self.n_frames)
+        out = np.zeros((self.U, len(points)), dtype=self.lib.score_dtype)
+        pending = []
+        unique = 0
+        be, lib_ = self.be, self.lib
+        for key, g in groups.items():
+            n_fft, hop = key[0], key[1]
+            Y = self.stft(n_fft, hop)
+            N, tv = self.noise(key)
+            rows = g["rows"]
+            unique += len(rows)
+            params = be.from_host(_lib.pack_params(rows))
+            scores = be.empty((self.U * len(rows) * self.lib.score_dtype.itemsize,), np.uint8)
+            total = self.U * len(rows)
+            chunk = min(self.chunk_items, total)
+            wav = self._workspace("wav", chunk * self.L * np.dtype(self.real).itemsize)
+            nbytes = lib_.score_workspace_bytes(chunk, self.L, SR)
+            ws = self._workspace("score", nbytes)
+            for i0 in range(0, total, chunk):
+                n = min(chunk, total - i0)
+                t0 = self._tick()
+                lib_.enhance_items(be.ptr(self.tables), alg, be.ptr(Y), be.ptr(N), int(tv), self.L, n_fft, hop,
+                                   be.ptr(params), len(rows), i0, n, be.ptr(wav), be.stream())
+                t1 = self._tick()
+                lib_.score_items(be.ptr(self.tables), be.ptr(wav), i0, n, len(rows), self.L, SR, be.ptr(self.clean),
+                                 be.ptr(self.cache), 1, be.ptr(scores), be.ptr(ws), nbytes, be.stream())
+                t2 = self._tick()
+                self._record(("enhance", alg, n_fft, hop, key[2]), n, t0, t1)
+                self._record(("score", alg, n_fft, hop, key[2]), n, t1, t2)
+                self.launches += 3
+            pending.append((g, scores, params))
+        for g, scores, _ in pending:
+            sc = be.view_bytes_as(scores, self.lib.score_dtype).reshape(self.U, len(g["rows"]))
+            for r, members in enumerate(g["members"]):
+                out[:, members] = sc[:, r:r + 1]
+        self.last_unique = unique
+        return out
+
+    def sweep_ranges(self, alg_name, param_ranges):
+        points = grid_points(param_ranges)
+        return points, self.sweep(alg_name, points)
+
+    # ------------------------------------------------------------------ single candidates
+    def enhance(self, alg_name, points):
+        """Raw enhanced waveforms [U, len(points), L] (host, library precision) - used for the
+        winners' artefacts and by the per-call drop-in functions."""
+        alg = ALGORITHM_IDS[alg_name] if isinstance(alg_name, str) else int(alg_name)
+        groups = plan(alg, points, self.n_frames)
+        out = np.zeros((self.U, len(points), self.L), dtype=self.real)
+        be, lib_ = self.be, self.lib
+        for key, g in groups.items():
+            n_fft, hop = key[0], key[1]
+            Y = self.stft(n_fft, hop)
+            N, tv = self.noise(key)
+            rows = g["rows"]
+            params = be.from_host(_lib.pack_params(rows))
+            wav = be.empty((self.U * len(rows), self.L), self.real)
+            lib_.enhance(be.ptr(self.tables), alg, be.ptr(Y), be.ptr(N), int(tv), self.U, self.L, n_fft, hop,
+                         be.ptr(params), len(rows), be.ptr(wav), be.stream())
+            self.launches += 1
+            host = be.to_host(wav).reshape(self.U, len(rows), self.L)
+            for r, members in enumerate(g["members"]):
+                out[:, members, :] = host[:, r:r + 1, :]
+        return out
+
+    def score_waveforms(self, wav, finalize=True):
+        """Scores arbitrary waveforms [U, C, L] against this batch's clean signals."""
+        wav = np.ascontiguousarray(wav, dtype=self.real)
+        U, C, L = wav.shape
+        if U != self.U or L != self.L:
+            raise ValueError("waveforms must be [U, C, L] for this batch")
+        be, lib_ = self.be, self.lib
+        dev = be.from_host(wav)
+        scores = be.empty((U * C * self.lib.score_dtype.itemsize,), np.uint8)
+        nbytes = lib_.score_workspace_bytes(U * C, L, SR)
+        ws = self._workspace("score", nbytes)
+        lib_.score(be.ptr(self.tables), be.ptr(dev), U, C, L, SR, be.ptr(self.clean), be.ptr(self.cache),
+                   int(finalize), be.ptr(scores), be.ptr(ws), nbytes, be.stream())
+        self.launches += 2
+        return be.view_bytes_as(scores, self.lib.score_dtype).reshape(U, C)
+
+    def baseline(self):
+        """STOI / SNR of the unprocessed noisy signals (``optimize_parameters`` ``:116-118``)."""
+        return self.score_waveforms(self.be.to_host(self.noisy)[:, None, :], finalize=False)[:, 0]
+
+    def noise_psd_host(self, method, n_fft, hop, percentile, eps):
+        """(bins, 1) or (bins, frames) float64 per utterance, reference orientation."""
+        from .grid import noise_key
+        key = noise_key({"n_fft": n_fft, "hop_length": hop, "noise_method": method,
+                         "noise_percentile": percentile}, eps)
+        N, tv = self.noise(key)
+        host = self.be.to_host(N).astype(np.float64)
+        nb = n_fft // 2 + 1
+        if tv:
+            return [host[u, :, :nb].T.copy() for u in range(self.U)]
+        return [host[u, :nb, None].copy() for u in range(self.U)]
+
+
+def finalize_host(enhanced, lag, length):
+    """``finalize_enhanced`` for a winner whose lag the device already estimated: shift, match
+    length, clip (``speech_enhancement_comparison.py:62-67,29-36,105``)."""
+    x = np.asarray(enhanced, dtype=np.float64)
+    if lag > 0:
+        x = np.pad(x, (lag, 0))
+    elif lag < 0:
+        x = x[-lag:]
+    if len(x) > length:
+        x = x[:length]
+    elif len(x) < length:
+        x = np.pad(x, (0, length - len(x)))
+    return np.clip(x, -1.0, 1.0)

@@ -1,0 +1,110 @@
+"""Host-side grid logic: enumeration, grouping, dead-parameter dedupe, param packing, selection.
+
+Mirrors ``Code/speech_enhancement_comparison.py``: candidates are the ``itertools.product`` of
+the range dict in insertion order, last key fastest (``:149-150``); the three winners come from
+a sequential scan with hysteresis (``:186-216``) and therefore stay on the host, in grid order.
+"""
+from collections import OrderedDict
+from itertools import product
+
+from ._lib import ALG_MMSE, ALG_OMLSA, ALG_SS, ALG_WIENER
+
+#: reference algorithm names (``speech_enhancement_comparison.py:395-401``) -> C-ABI ids
+ALGORITHM_IDS = {"spectralSubtractor": ALG_SS, "wiener": ALG_WIENER, "mmse": ALG_MMSE, "omlsa": ALG_OMLSA}
+NOISE_METHODS = ("percentile", "min_tracking", "true_noise")
+TOL = {"stoi": 1e-6, "pesq": 1e-3, "balance": 1e-5}      # :186, :196, :206
+
+
+def alg_eps(alg):
+    """Epsilon each reference entry point hands to ``noise_estimation`` (``mmse.py:17`` vs the rest)."""
+    return 1e-12 if alg == ALG_MMSE else 1e-10
+
+
+def grid_points(param_ranges):
+    names = list(param_ranges.keys())
+    return [dict(zip(names, values)) for values in product(*param_ranges.values())]
+
+
+def noise_key(point, eps):
+    """Cache key of the noise PSD a point needs.  ``min_tracking`` and ``true_noise`` ignore
+    ``noise_percentile`` (``Code/noise_estimation.py:60-95,115-155``)."""
+    method = point["noise_method"]
+    if method not in NOISE_METHODS:
+        raise ValueError(f"Unbekannte Methode: {method}")
+    pct = float(point["noise_percentile"]) if method == "percentile" else None
+    return (int(point["n_fft"]), int(point["hop_length"]), method, pct, eps)
+
+
+def param_row(alg, point, noise_time_varying):
+    """The ``cse_params.v`` row of one grid point (layout documented in include/cse.h).
+
+    ``noise_mu`` only acts when the noise PSD is time-varying and the method is not
+    ``true_noise`` (``mmse.py:48``, ``advanced_mmse.py:60``); otherwise it is packed as -1 so
+    that candidates differing only in that dead parameter collapse onto one device candidate.
+    """
+    smooth = noise_time_varying and point["noise_method"] != "true_noise"
+    if alg == ALG_SS:
+        return (float(point["alpha"]), float(point["beta"]))
+    if alg == ALG_WIENER:
+        return (float(point["alpha"]), float(point["gain_floor"]))
+    if alg == ALG_MMSE:
+        mu = float(point.get("noise_mu", 0.98)) if smooth else -1.0
+        return (float(point["alpha"]), float(point["ksi_min"]), float(point["gain_min"]),
+                float(point["gain_max"]), mu)
+    if alg == ALG_OMLSA:
+        mu = float(point["noise_mu"]) if smooth else -1.0
+        return (float(point["alpha"]), float(point["ksi_min"]), float(point["gain_floor"]), mu,
+                float(point["q"]), float(point.get("v_max", 80.0)))
+    raise ValueError(f"unknown algorithm id {alg}")
+
+
+def plan(alg, points, n_frames_of):
+    """Group grid points by the noise PSD they share and dedupe identical device candidates.
+
+    Returns an ordered dict ``noise_key -> {"rows": [unique param rows], "members": [[grid
+    indices sharing row r], ...]}``.  ``n_frames_of(n_fft, hop)`` tells whether the PSD is
+    time-varying (the short-signal rule of ``noise_estimation.py:194-195`` makes it static).
+    """
+    groups = OrderedDict()
+    eps = alg_eps(alg)
+    for i, pt in enumerate(points):
+        key = noise_key(pt, eps)
+        n_frames = n_frames_of(key[0], key[1])
+        tv = key[2] != "percentile" and n_frames >= 5
+        row = param_row(alg, pt, tv)
+        g = groups.setdefault(key, {"rows": [], "members": [], "index": {}, "time_varying": tv})
+        r = g["index"].get(row)
+        if r is None:
+            r = len(g["rows"])
+            g["index"][row] = r
+            g["rows"].append(row)
+            g["members"].append([])
+        g["members"][r].append(i)
+    for g in groups.values():
+        del g["index"]
+    return groups
+
+
+def combined_score(stoi, pesq):
+    """``calculate_combined_speech_score`` (``Code/evaluation_metrics.py:104-114``)."""
+    if stoi is None:
+        stoi = 0
+    if pesq is None:
+        pesq = 0
+    return 0.5 * stoi + 0.5 * (max(0, pesq) / 4.5)
+
+
+def select_best(points, stoi, pesq, snr, valid):
+    """Sequential best-of with hysteresis over candidates in grid order; ``pesq[i]`` may be None
+    (candidate skipped, ``:180-181``).  Returns ``{criterion: dict}`` with index None if no
+    candidate qualified."""
+    best = {c: {"index": None, "score": -1, "params": {}} for c in TOL}
+    for i in range(len(points)):
+        if not valid[i] or pesq[i] is None or stoi[i] is None:
+            continue
+        vals = {"stoi": stoi[i], "pesq": pesq[i], "balance": combined_score(stoi[i], pesq[i])}
+        for c in TOL:
+            if vals[c] > best[c]["score"] + TOL[c]:
+                best[c] = {"index": i, "score": vals[c], "params": dict(points[i]),
+                           "stoi": stoi[i], "pesq": pesq[i], "snr": snr[i]}
+    return best

@@ -1,0 +1,64 @@
+"""Dataset-level sweep: every algorithm x every grid point x every utterance pair.
+
+``sweep_dataset`` is the batched form of the reference's double loop
+``for pair: for algorithm: run_algorithm_on_pair`` (``Code/speech_enhancement_comparison.py:441-458``):
+it takes HOST arrays, moves them to the device once, runs the device sweep and returns the
+score tables (and, optionally, the reference's three winners per (utterance, algorithm)).
+"""
+import numpy as np
+
+from .engine import SweepEngine
+from .grid import grid_points, select_best
+from .parameter_ranges import (param_ranges_mmse, param_ranges_omlsa, param_ranges_ss,
+                               param_ranges_wiener)
+
+#: the reference's algorithm order (``speech_enhancement_comparison.py:395-401``)
+DEFAULT_GRIDS = (("spectralSubtractor", param_ranges_ss), ("mmse", param_ranges_mmse),
+                 ("wiener", param_ranges_wiener), ("omlsa", param_ranges_omlsa))
+
+
+def nominal_and_unique(grids=DEFAULT_GRIDS):
+    from .grid import ALGORITHM_IDS, plan
+    nominal = unique = 0
+    for name, ranges in grids:
+        pts = grid_points(ranges)
+        nominal += len(pts)
+        unique += sum(len(g["rows"]) for g in plan(ALGORITHM_IDS[name], pts, lambda a, b: 376).values())
+    return nominal, unique
+
+
+def run_engine(engine, grids=DEFAULT_GRIDS):
+    """Device part only: {alg: structured scores [U, n_points]} (+ points)."""
+    scores, points, unique = {}, {}, 0
+    for name, ranges in grids:
+        pts = grid_points(ranges)
+        scores[name] = engine.sweep(name, pts)
+        points[name] = pts
+        unique += engine.last_unique
+    return scores, points, unique
+
+
+def select_all(scores, points, pesq=None):
+    """The reference's three winners per (utterance, algorithm), by its sequential scan.
+    ``pesq[alg][u][i]`` may be injected; otherwise PESQ is 0.0 (see speech_enhancement_comparison)."""
+    out = {}
+    for name, sc in scores.items():
+        rows = []
+        for u in range(sc.shape[0]):
+            valid = (sc[u]["flags"] & 1) != 0
+            snr = [float("inf") if f & 4 else float(v) for v, f in zip(sc[u]["snr"], sc[u]["flags"])]
+            pq = pesq[name][u] if pesq is not None else [0.0] * sc.shape[1]
+            rows.append(select_best(points[name], [float(v) for v in sc[u]["stoi"]], pq, snr, valid))
+        out[name] = rows
+    return out
+
+
+def sweep_dataset(clean, noisy, grids=DEFAULT_GRIDS, sr=16000, select=True, chunk_items=1184, engine_kwargs=None):
+    """clean, noisy: host arrays [U, L] (equal-length, 16 kHz, pair-aligned).
+
+    Returns ``{"scores", "points", "nominal", "unique", "selection", "engine"}``."""
+    eng = SweepEngine(clean, noisy, sr=sr, chunk_items=chunk_items, **(engine_kwargs or {}))
+    scores, points, unique = run_engine(eng, grids)
+    nominal = sum(len(p) for p in points.values()) * eng.U
+    return {"scores": scores, "points": points, "nominal": nominal, "unique": unique * eng.U,
+            "selection": select_all(scores, points) if select else None, "engine": eng}

@@ -133,6 +133,17 @@ int cse_sweep(const void* tables, int algorithm, const void* Y, const void* N, i
               int sr, const void* clean, const void* cache, cse_score_t* scores,
               int chunk_items, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Chunk-level forms of the two halves of cse_sweep, for callers that drive the chunk loop
+ * themselves (the Python engine does, to bracket each kernel family with CUDA events).
+ * Items are indices into the utterance-major (utterance, param) product; `out` / `wav` hold only
+ * the n_items waveforms of the chunk, `scores` is the base of the full [n_utts*n_params] table. */
+int cse_enhance_items(const void* tables, int algorithm, const void* Y, const void* N, int noise_tv,
+                      int length, int n_fft, int hop, const cse_params* params, int n_params,
+                      int item0, int n_items, void* out, void* stream);
+int cse_score_items(const void* tables, const void* wav, int item0, int n_items, int per_utt,
+                    int length, int sr, const void* clean, const void* cache, int finalize,
+                    cse_score_t* scores, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Host-side probe used by the tests: evaluates the special-function fits the gain kernels
  * inline (which = 0: exp(-v/2)[(1+v)I0(v/2)+vI1(v/2)] of Code/mmse.py:92-96; 1: E1(v) of
  * Code/advanced_mmse.py:103) at x[0..n) in the library's precision. */

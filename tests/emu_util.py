@@ -104,3 +104,42 @@ class Emu:
         self.lib.sweep(ptr(self.tables), alg, ptr(Y), ptr(N), int(N.ndim == 3), U, L, n_fft, hop, ptr(params),
                        len(rows), 16000, ptr(clean), ptr(cache), ptr(scores), chunk, ptr(ws), ws.nbytes, None)
         return scores.reshape(U, len(rows))
+
+
+class NumpyBackend:
+    """Engine backend over host memory for the thread-emulated library (tests only)."""
+
+    def empty(self, shape, dtype):
+        return np.empty(shape, dtype=dtype)
+
+    def zeros(self, shape, dtype):
+        return np.zeros(shape, dtype=dtype)
+
+    def from_host(self, arr, pinned=False):
+        return np.array(arr, copy=True, order="C")
+
+    def to_host(self, buf):
+        return np.array(buf, copy=True)
+
+    def ptr(self, buf):
+        return ptr(buf)
+
+    def stream(self):
+        return None
+
+    def synchronize(self):
+        pass
+
+    def view_bytes_as(self, buf, dtype):
+        return buf.view(dtype)
+
+
+def use_emulated_runtime(fp64=False):
+    """Point SweepEngine's default runtime at the emulation build (CPU tests of host logic)."""
+    from classical_speech_enhancement_b200 import engine
+    engine.configure_runtime(lib=emu_lib(fp64), backend_factory=NumpyBackend)
+
+
+def use_product_runtime():
+    from classical_speech_enhancement_b200 import engine
+    engine.configure_runtime(None, None)

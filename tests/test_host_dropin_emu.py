@@ -1,0 +1,123 @@
+"""Host-side drop-in layer (grid planning, dedupe, selection, reference-named entry points)
+exercised end to end without a GPU: the engine runs on the thread-emulated kernels."""
+import numpy as np
+import pytest
+
+import oracle
+from oracle.noise import noise_psd
+from classical_speech_enhancement_b200 import grid
+from classical_speech_enhancement_b200 import parameter_ranges as pr
+from classical_speech_enhancement_b200.synth import make_pair
+from tests.emu_util import use_emulated_runtime, use_product_runtime
+
+
+@pytest.fixture(scope="module", autouse=True)
+def emulated():
+    use_emulated_runtime()
+    yield
+    use_product_runtime()
+
+
+def f32(x):
+    return x.astype(np.float32).astype(np.float64)
+
+
+def test_plan_dedupes_dead_parameters():
+    for ranges, alg, nominal, unique in ((pr.param_ranges_ss, 0, 720, 540), (pr.param_ranges_mmse, 2, 1920, 1440),
+                                         (pr.param_ranges_wiener, 1, 192, 144), (pr.param_ranges_omlsa, 3, 6912, 2880)):
+        pts = grid.grid_points(ranges)
+        groups = grid.plan(alg, pts, lambda n_fft, hop: 376)
+        assert len(pts) == nominal
+        assert sum(len(g["rows"]) for g in groups.values()) == unique
+        assert sorted(i for g in groups.values() for m in g["members"] for i in m) == list(range(nominal))
+        assert len(groups) == 12          # 4 STFT shapes x (2 percentile PSDs + 1 min_tracking PSD)
+
+
+def test_per_call_functions_match_oracle():
+    from classical_speech_enhancement_b200.advanced_mmse import advanced_mmse
+    from classical_speech_enhancement_b200.mmse import mmse
+    from classical_speech_enhancement_b200.noise_estimation import noise_estimation
+    from classical_speech_enhancement_b200.spectral_subtractor import spectral_subtraction
+    from classical_speech_enhancement_b200.wiener_filter import wiener_filter
+    c, n = make_pair(2, 5000)
+    c, n = f32(c), f32(n)
+    kw = dict(n_fft=512, hop_length=128, noise_percentile=10.0)
+    pairs = [
+        (spectral_subtraction, oracle.spectral_subtraction, dict(alpha=2.0, beta=0.05, noise_method="true_noise", clean_audio=c)),
+        (wiener_filter, oracle.wiener_filter, dict(alpha=0.95, gain_floor=0.02, noise_method="percentile")),
+        (mmse, oracle.mmse, dict(alpha=0.98, ksi_min=0.01, gain_min=0.1, gain_max=1.0, noise_method="min_tracking")),
+        (advanced_mmse, oracle.advanced_mmse, dict(alpha=0.8, ksi_min=0.005, q=0.5, noise_mu=0.98, gain_floor=0.2,
+                                                   noise_method="min_tracking")),
+    ]
+    for ours, ref, extra in pairs:
+        a = ours(n, 16000, **kw, **extra)
+        b = ref(n, 16000, **kw, **extra)
+        assert a.dtype == np.float64 and a.shape == b.shape
+        assert np.abs(a - b).max() / np.abs(b).max() < 1e-5
+    stereo = np.stack([n, n], axis=1)
+    assert np.allclose(wiener_filter(stereo, 16000, 512, 128, 0.95, 0.02, 10.0, "percentile"),
+                       wiener_filter(n, 16000, 512, 128, 0.95, 0.02, 10.0, "percentile"))
+    N = noise_estimation(n, 16000, method="min_tracking", n_fft=512, hop_length=128, percentile=10.0, eps=1e-10)
+    ref = noise_psd(n, "min_tracking", 512, 128, eps=1e-10)
+    assert N.shape == ref.shape and np.abs(N - ref).max() / ref.max() < 2e-6
+    N = noise_estimation(n, 16000, method="percentile", n_fft=512, hop_length=128, percentile=20.0, eps=1e-10)
+    assert N.shape == (257, 1)
+    with pytest.raises(ValueError):
+        noise_estimation(n, 16000, method="nope", n_fft=512, hop_length=128)
+    with pytest.raises(ValueError):
+        spectral_subtraction(n, 16000, 1.0, 0.01, 512, 128, 10.0, "true_noise")
+
+
+def test_metrics_match_oracle():
+    from classical_speech_enhancement_b200.evaluation_metrics import (calculate_combined_speech_score,
+                                                                      calculate_snr, calculate_stoi)
+    c, n = make_pair(3, 12000)
+    c, n = f32(c), f32(n)
+    assert abs(calculate_stoi(c, n, 16000) - oracle.stoi(c, n, 16000)) < 1e-5
+    assert abs(calculate_snr(c, n) - oracle.global_snr(c, n)) < 1e-4
+    assert calculate_snr(c, c) == float("inf")
+    assert calculate_combined_speech_score(0.8, None) == 0.4
+    assert abs(calculate_combined_speech_score(0.8, 2.25) - 0.65) < 1e-12
+
+
+SMALL_WIENER = {"alpha": [0.90, 0.98], "gain_floor": [0.01, 0.1], "n_fft": [512], "hop_length": [128, 256],
+                "noise_percentile": [10.0, 20.0], "noise_method": ["percentile", "min_tracking"]}
+
+
+def test_optimize_parameters_matches_oracle_sweep():
+    """Selections identical to the oracle's sequential scan, with an injected PESQ scorer."""
+    from classical_speech_enhancement_b200.speech_enhancement_comparison import optimize_parameters
+    from classical_speech_enhancement_b200.wiener_filter import wiener_filter
+    c, n = make_pair(5, 11000)
+    c, n = f32(c), f32(n)
+
+    def fake_pesq(clean, deg, sr):          # deterministic stand-in, sensitive to the waveform
+        return 1.0 + 3.0 * float(np.clip(np.corrcoef(clean, deg)[0, 1], 0, 1))
+
+    pts, scores, best = oracle.sweep_one_pair(c, n, 16000, oracle.wiener_filter, SMALL_WIENER, pesq_fn=fake_pesq)
+    out = optimize_parameters(c, n, 16000, wiener_filter, SMALL_WIENER, pesq_scorer=fake_pesq, verbose=False)
+    for crit in ("stoi", "pesq", "balance"):
+        assert out[crit]["params"] == best[crit]["params"], crit
+        assert abs(out[crit]["score"] - best[crit]["score"]) < 1e-4
+        assert abs(out[crit]["snr"] - best[crit]["snr"]) < 1e-3
+    assert abs(out["baseline"]["stoi"] - oracle.stoi(c, n, 16000)) < 1e-5
+    ref_wave = [s for s, p in zip(scores, pts) if p == best["stoi"]["params"]][0]
+    assert set(out) == {"stoi", "pesq", "balance", "baseline", "improvements"}
+    assert set(out["balance"]) == {"score", "params", "enhanced", "stoi", "pesq", "snr"}
+    assert out["stoi"]["enhanced"].shape == c.shape and np.abs(out["stoi"]["enhanced"]).max() <= 1.0
+    assert ref_wave is not None
+
+
+def test_run_algorithm_on_pair_row_schema(tmp_path):
+    from classical_speech_enhancement_b200.speech_enhancement_comparison import run_algorithm_on_pair
+    from classical_speech_enhancement_b200.spectral_subtractor import spectral_subtraction
+    c, n = make_pair(6, 10000)
+    ranges = {"alpha": [1.0, 3.0], "beta": [0.01], "n_fft": [512], "hop_length": [128],
+              "noise_percentile": [10.0], "noise_method": ["true_noise", "min_tracking"]}
+    row = run_algorithm_on_pair("spectralSubtractor", spectral_subtraction, ranges, f32(c), f32(n), 16000,
+                                str(tmp_path), "synth_006", pesq_scorer=lambda a, b, sr: 2.0, verbose=False)
+    assert list(row)[:6] == ["alg", "stem", "sr", "stoi_noisy", "pesq_noisy", "snr_noisy"]
+    assert row["best_params_stoi"]["noise_method"] == "true_noise"
+    assert sorted(p.name for p in tmp_path.iterdir()) == [
+        "synth_006_spectralSubtractor_optimized_balanced.wav", "synth_006_spectralSubtractor_optimized_pesq.wav",
+        "synth_006_spectralSubtractor_optimized_stoi.wav"]
