@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Benchmark of the enhancement-and-scoring sweep (BASELINE.json metric: enhanced
+utterance-configs/s at 1/2/4/8 B200, plus achieved HBM GB/s against the measured peak).
+
+One "step" = one pass of the whole hot path over the whole synthetic test set: for every
+utterance pair, all four algorithms x the full ``parameter_ranges.py`` grids (9744 nominal /
+5004 unique grid points): STFTs, noise PSDs, clean-side scoring caches, gain + ISTFT,
+alignment, STOI and SNR for every candidate.  With N GPUs the utterances are sharded in
+contiguous blocks (strong scaling: the job is fixed at --utts utterances) and the score tables
+are all-gathered over NCCL at the end of the step.
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the CPU path (oracle port of the reference) on the host cores
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the byte model behind `roofline`.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "enhanced utterance-configs/sec"
+UNIT = "utterance-configs/s"
+SR = 16000
+
+
+# ------------------------------------------------------------------------------ data
+def _pair(args):
+    from classical_speech_enhancement_b200.synth import make_pair
+    u, L = args
+    c, n = make_pair(u, L)
+    return c.astype(np.float32), n.astype(np.float32)
+
+
+def make_shard(first, count, L):
+    """Synthetic pairs first..first+count-1 (seed 1000+u each), generated on the host cores."""
+    import multiprocessing as mp
+    if count == 0:
+        return np.zeros((0, L), np.float32), np.zeros((0, L), np.float32)
+    procs = max(1, min(count, (os.cpu_count() or 2) - 1, 32))
+    if procs > 1:
+        with mp.get_context("fork").Pool(procs) as pool:
+            out = pool.map(_pair, [(first + i, L) for i in range(count)], chunksize=4)
+    else:
+        out = [_pair((first + i, L)) for i in range(count)]
+    return np.stack([o[0] for o in out]), np.stack([o[1] for o in out])
+
+
+# ------------------------------------------------------------------------------ byte model
+def config_bytes(n_fft, hop, method, L, real_bytes=4):
+    """Algorithmic bytes of ONE utterance-config: read Y, read the noise PSD, write the
+    enhanced waveform, read it back for scoring, 16 B of scores.  Returns (total, enhance part, score part)."""
+    nb, nf = n_fft // 2 + 1, 1 + L // hop
+    y = 2 * real_bytes * nb * nf
+    n = real_bytes * nb * (1 if method == "percentile" else nf)
+    return y + n + 2 * real_bytes * L + 16, y + n + real_bytes * L, real_bytes * L + 16
+
+
+def grid_mean_bytes(L):
+    from classical_speech_enhancement_b200.grid import grid_points
+    from classical_speech_enhancement_b200.sweep import DEFAULT_GRIDS
+    tot = cnt = 0
+    for _, ranges in DEFAULT_GRIDS:
+        for p in grid_points(ranges):
+            tot += config_bytes(p["n_fft"], p["hop_length"], p["noise_method"], L)[0]
+            cnt += 1
+    return tot / cnt, cnt
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------ CPU path (oracle port)
+def _cpu_task(task):
+    """One utterance-config through the reference's per-candidate procedure (no caching), no PESQ."""
+    import oracle
+    from oracle.search import score_candidate
+    from classical_speech_enhancement_b200.synth import make_pair
+    alg, point, u, L = task
+    c, n = make_pair(u, L)
+    c = c.astype(np.float32).astype(np.float64)
+    n = n.astype(np.float32).astype(np.float64)
+    t = time.perf_counter()
+    fn = oracle.ALGORITHMS[alg]
+    enh = fn(n, SR, **point)
+    sc = score_candidate(c, enh, SR)
+    return time.perf_counter() - t, (sc["stoi"] if sc else None)
+
+
+def cpu_sample(n_tasks, L, seed=0):
+    """Random (algorithm, grid point, utterance) triples drawn uniformly from the nominal 9744-point grid."""
+    from classical_speech_enhancement_b200.grid import grid_points
+    from classical_speech_enhancement_b200.sweep import DEFAULT_GRIDS
+    allpts = [(name, p) for name, ranges in DEFAULT_GRIDS for p in grid_points(ranges)]
+    rng = np.random.default_rng(seed)
+    idx = rng.choice(len(allpts), n_tasks, replace=False)
+    return [(allpts[i][0], allpts[i][1], int(rng.integers(0, 824)), L) for i in idx]
+
+
+def cpu_baseline_single_thread(L, n_tasks=160):
+    for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ.setdefault(v, "1")
+    tasks = cpu_sample(n_tasks, L, seed=0)
+    t = time.perf_counter()
+    for task in tasks:
+        _cpu_task(task)
+    dt = time.perf_counter() - t
+    return {"value": n_tasks / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{n_tasks} random (algorithm, grid point, utterance) configs of the {L}-sample workload, "
+                      f"seed 0, fp64 numpy/scipy oracle, no cross-candidate caching, no PESQ, {dt:.1f} s"}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path.  The reference itself cannot be
+    imported (librosa/pystoi/pesq absent), so this is the oracle port, on all host cores."""
+    import multiprocessing as mp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[v] = "1"
+    cores = os.cpu_count() or 1
+    per_step = max(64, 4 * cores)
+    L = args.length
+    mean_bytes, nominal = grid_mean_bytes(L)
+    with mp.get_context("fork").Pool(cores) as pool:
+        times = []
+        for step in range(args.warmup + args.steps):
+            tasks = cpu_sample(per_step, L, seed=step)
+            t = time.perf_counter()
+            pool.map(_cpu_task, tasks, chunksize=1)
+            dt = time.perf_counter() - t
+            if step >= args.warmup:
+                times.append(dt)
+    total = sum(times)
+    value = per_step * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, nominal, None),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per_step} random configs of the workload per step on {cores} processes "
+                                   "(fp64 numpy/scipy oracle restatement of the reference; PESQ excluded)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, nominal_points, unique_points):
+    return {"workload": f"C5: all four algorithms x full parameter_ranges.py grid ({nominal_points} nominal grid "
+                        f"points/utterance) x {args.utts} synthetic 16 kHz pairs of {args.length} samples, "
+                        "enhance + finalize + STOI + SNR per candidate (PESQ excluded, host-side)",
+            "utterances": args.utts, "length": args.length, "grid_points_nominal": nominal_points,
+            "grid_points_unique": unique_points, "chunk_items": args.chunk,
+            "cache_hygiene": "inputs larger than L2: waveforms + spectrogram / noise-PSD caches of the shard are "
+                             "GBs and every step recomputes them from the raw signals; candidate waveforms are "
+                             "rewritten every chunk",
+            "parallelism": f"utterance-sharded x{args.gpus}"}
+
+
+# ------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--utts", type=int, default=824)
+    ap.add_argument("--length", type=int, default=48000)
+    ap.add_argument("--chunk", type=int, default=1184)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from classical_speech_enhancement_b200 import sweep as sw
+    from classical_speech_enhancement_b200.distributed import gather_scores, shard_bounds
+    from classical_speech_enhancement_b200.engine import SweepEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+
+    L = args.length
+    b = shard_bounds(args.utts, world)
+    clean_h, noisy_h = make_shard(b[rank], b[rank + 1] - b[rank], L)
+    clean_pin = torch.from_numpy(clean_h).pin_memory()
+    noisy_pin = torch.from_numpy(noisy_h).pin_memory()
+    mean_bytes, nominal_points = grid_mean_bytes(L)
+    _, unique_points = sw.nominal_and_unique()
+    total_configs = args.utts * nominal_points
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm: inputs already in HBM
+    eng = SweepEngine(clean_pin.numpy(), noisy_pin.numpy(), chunk_items=args.chunk)
+
+    def step_resident():
+        eng.reset()
+        scores, _, _ = sw.run_engine(eng)
+        if world > 1:
+            for name in scores:
+                gather_scores(scores[name], args.utts, device=device)
+        return scores
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    eng.enable_timing(True)
+    launches0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for _ in range(args.steps):
+        scores = step_resident()
+    ev1.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    launches = eng.launches - launches0
+    timing = eng.timing_summary()
+    eng.enable_timing(False)
+    t = torch.tensor([max(dev_ms / 1e3, 0.0), wall], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_s, wall_s = float(t[0]), float(t[1])
+    step_s = max(dev_s, 1e-9) / args.steps
+
+    # ---------------- end-to-end arm: host buffers in, host score tables out, every step
+    def step_e2e():
+        out = sw.sweep_dataset(clean_pin.numpy(), noisy_pin.numpy(), select=False, chunk_items=args.chunk)
+        if world > 1:
+            for name in out["scores"]:
+                gather_scores(out["scores"][name], args.utts, device=device)
+        return out
+
+    del eng
+    torch.cuda.empty_cache()
+    step_e2e()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 2))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out = step_e2e()
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te[0]) / e2e_steps
+    h2d = out["engine"].h2d_bytes
+    d2h = sum(v.nbytes for v in out["scores"].values())
+
+    # ---------------- roofline of the dominant kernel family (events around every chunk launch)
+    fam = {}
+    for (kind, alg, n_fft, hop, method), (items, ms) in timing.items():
+        _, eb, sb = config_bytes(n_fft, hop, method, L)
+        f = fam.setdefault(kind, [0.0, 0.0, 0])
+        f[0] += items * (eb if kind == "enhance" else sb)
+        f[1] += ms
+        f[2] += items
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    dom = max(fam, key=lambda k: fam[k][1]) if fam else None
+    roofline = None
+    if dom:
+        by, ms, items = fam[dom]
+        ach = by / (ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": {"enhance": "enhance_kernel<ALG,LOG2N,F> (gain + ISTFT)",
+                                               "score": "align_kernel + stoi_kernel"}[dom],
+                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": peak_kind,
+                    "share_of_step": ms / (dev_ms if dev_ms > 0 else 1.0),
+                    "families": {k: {"ms": v[1], "algorithmic_GBps": v[0] / (v[1] * 1e-3) / 1e9 if v[1] else None,
+                                     "items": v[2]} for k, v in fam.items()},
+                    "whole_path": {"bytes_per_config": mean_bytes,
+                                   "achieved": total_configs / step_s * mean_bytes / 1e9 / world,
+                                   "frac": total_configs / step_s * mean_bytes / 1e9 / world / peak,
+                                   "note": "per GPU; nominal configs x grid-mean algorithmic bytes (SURVEY 8d)"}}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline_single_thread(L)
+        line = {
+            "metric": METRIC, "value": total_configs / step_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, nominal_points, unique_points),
+            "unique_value": args.utts * unique_points / step_s,
+            "e2e": {"value": total_configs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s},
+            "gpu_launches": int(launches), "wall_ms_per_step": 1e3 * wall_s / args.steps,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -100,22 +100,36 @@ class SweepEngine:
         be, lib_ = self.be, self.lib
         self.tables = be.empty((lib_.tables_bytes(),), np.uint8)
         lib_.tables_init(be.ptr(self.tables), be.stream())
-        self.clean = be.from_host(clean.astype(self.real))
-        self.noisy = be.from_host(noisy.astype(self.real))
+        self.clean = be.from_host(np.ascontiguousarray(clean, dtype=self.real))
+        self.noisy = be.from_host(np.ascontiguousarray(noisy, dtype=self.real))
         self.h2d_bytes = 2 * clean.size * np.dtype(self.real).itemsize
         self._stft = {}
         self._noise = {}
         self._ws = {}
         self.launches = 0
-        if not self.has_clean or not prepare_scoring:
-            self.cache = None
-            return
-        rec = lib_.clean_cache_bytes(self.L, sr)
-        self.cache = be.zeros((self.U * rec,), np.uint8)
-        ws = self._workspace("clean", lib_.clean_workspace_bytes(self.U, self.L, sr))
-        lib_.prepare_clean(be.ptr(self.tables), be.ptr(self.clean), self.U, self.L, sr, be.ptr(self.cache),
-                           be.ptr(ws), self._ws["clean"][1], be.stream())
+        self.cache = None
+        self.sr = sr
+        if self.has_clean and prepare_scoring:
+            self.prepare_scoring()
+
+    def prepare_scoring(self):
+        """(Re)build the clean-side scoring caches (alignment spectra, VAD list, band envelopes)."""
+        be, lib_ = self.be, self.lib
+        rec = lib_.clean_cache_bytes(self.L, self.sr)
+        if self.cache is None:
+            self.cache = be.zeros((self.U * rec,), np.uint8)
+        nbytes = lib_.clean_workspace_bytes(self.U, self.L, self.sr)
+        ws = self._workspace("clean", nbytes)
+        lib_.prepare_clean(be.ptr(self.tables), be.ptr(self.clean), self.U, self.L, self.sr, be.ptr(self.cache),
+                           be.ptr(ws), nbytes, be.stream())
         self.launches += 3
+
+    def reset(self):
+        """Forget every derived cache (STFTs, noise PSDs, clean-side scoring caches) but keep the
+        waveforms resident: the next sweep redoes the whole job from the raw signals."""
+        self.drop_caches()
+        if self.has_clean:
+            self.prepare_scoring()
 
     # ------------------------------------------------------------------ optional kernel timing
     def enable_timing(self, on=True):
