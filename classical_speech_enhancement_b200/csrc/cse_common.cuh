@@ -59,6 +59,20 @@ CSE_HD real r_min(real a, real b) { return fminf(a, b); }
 CSE_HD real r_floor(real x) { return floorf(x); }
 CSE_HD real r_fma(real a, real b, real c) { return fmaf(a, b, c); }
 #endif
+// Fast forms for the fp32 gain rules: one MUFU op each (rcp / lg2 / ex2 / rsq), relative error
+// <= ~2e-6 over the ranges the gain rules use - far inside the 1e-4 waveform budget.  The FP64
+// build and the CPU emulation use the exact forms.
+#if defined(CSE_FP64) || defined(CSE_EMU)
+CSE_HD real r_rcp(real x) { return R(1) / x; }
+CSE_HD real r_fexp(real x) { return r_exp(x); }
+CSE_HD real r_flog(real x) { return r_log(x); }
+CSE_HD real r_fsqrt(real x) { return r_sqrt(x); }
+#else
+CSE_D real r_rcp(real x) { return __fdividef(1.0f, x); }
+CSE_D real r_fexp(real x) { return __expf(x); }
+CSE_D real r_flog(real x) { return __logf(x); }
+CSE_D real r_fsqrt(real x) { return x * rsqrtf(x); }
+#endif
 // numpy's maximum/minimum/clip propagate NaN, fmax/fmin drop it.  The reference relies on
 // that only through np.nan_to_num, which the gain kernels restate explicitly.
 CSE_HD real r_clip(real x, real lo, real hi) { return r_min(r_max(x, lo), hi); }

@@ -9,14 +9,17 @@
 // that sit between them address elements through __brev().  Several transforms ("batches")
 // laid out back to back are processed by one call so that every thread has butterflies to do.
 //
-// Storage index of logical element i is SIDX(i) = i + (i >> 3): one pad slot per 8 complex
-// values makes the last pass (thread owns 8 consecutive elements) and the strided middle
-// passes conflict-free for 8-byte accesses.
+// Storage index of logical element i is SIDX(i) = i + (i >> 4) + (i >> 8).  A brute-force bank
+// model over every access pattern used here (all radix passes for 128..8192 points, natural
+// order, k / M-k pairs of the real-FFT split, and bit-reversed reads) shows this padding is
+// conflict-free for 8-byte accesses everywhere except a 2-way conflict in the q=8 pass; the
+// first version (i + (i >> 3)) was 4- to 16-way conflicted on the bit-reversed reads
+// (profiles/r01_enhance_omlsa1024_ncu.md: 38 % of shared wavefronts were conflicts).
 #pragma once
 #include "cse_common.cuh"
 
-#define SIDX(i) ((i) + ((i) >> 3))
-#define CSE_FFT_STRIDE(n) ((n) + ((n) >> 3))
+#define SIDX(i) ((i) + ((i) >> 4) + ((i) >> 8))
+#define CSE_FFT_STRIDE(n) ((n) + ((n) >> 4) + ((n) >> 8) + 1)
 
 CSE_D real2 tw_load(const real2* __restrict__ tw, int idx) {
 #ifdef CSE_EMU

@@ -100,23 +100,23 @@ extern "C" int cse_stft_psd(const void* tables, const void* wav, const void* min
 }
 
 // ------------------------------------------------------------------ K3+K4 gain + ISTFT
-template <int ALG, int LOG2N, int F>
+template <int ALG, int LOG2N>
 static int launch_enhance(const EnhanceArgs& a, int n_items, void* stream) {
-    constexpr int NFFT = 1 << LOG2N, M = NFFT / 2;
-    const int W = NFFT + (F - 1) * a.hop;
-    const size_t smem = (size_t)F * (CSE_FFT_STRIDE(M) + 2) * sizeof(real2) + (size_t)(2 * W + 8) * sizeof(real);
-    auto kfn = enhance_kernel<ALG, LOG2N, F>;
+    typedef EnhanceCfg<LOG2N> C;
+    const int W = C::NFFT + (C::F - 1) * a.hop;
+    const size_t smem = (size_t)C::F * C::XST * sizeof(real2) + (size_t)(W + a.hop + 8) * sizeof(real);
+    auto kfn = enhance_kernel<ALG, LOG2N>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    CSE_LAUNCH(kfn, n_items, M, smem, stream, a);
+    CSE_LAUNCH(kfn, n_items, C::NT, smem, stream, a);
     return check_launch("enhance_kernel");
 }
 template <int ALG>
 static int dispatch_enhance(const EnhanceArgs& a, int n_fft, int n_items, void* stream) {
     switch (n_fft) {
-        case 256: return launch_enhance<ALG, 8, 4>(a, n_items, stream);
-        case 512: return launch_enhance<ALG, 9, 4>(a, n_items, stream);
-        case 1024: return launch_enhance<ALG, 10, 4>(a, n_items, stream);
-        default: return launch_enhance<ALG, 11, 2>(a, n_items, stream);
+        case 256: return launch_enhance<ALG, 8>(a, n_items, stream);
+        case 512: return launch_enhance<ALG, 9>(a, n_items, stream);
+        case 1024: return launch_enhance<ALG, 10>(a, n_items, stream);
+        default: return launch_enhance<ALG, 11>(a, n_items, stream);
     }
 }
 static real alg_eps(int algorithm) { return algorithm == CSE_ALG_MMSE ? R(1e-12) : R(1e-10); }

@@ -45,3 +45,22 @@ CSE_HD real cse_expint_e1(real v) {
     const real t = (R(2) / v - R(1.0125)) * R(1.0 / 0.9875);
     return clenshaw(c, t) * r_exp(-v) / v;
 }
+
+// Device-side fast variants used by the gain kernels (fp32: MUFU-based rcp / log / exp).
+CSE_D real cse_mmse_bessel_term_fast(real v) {
+    if (v <= R(16)) {
+        const real c[CSE_COEF_N(M_LO)] = CSE_COEF(M_LO);
+        return clenshaw(c, v * R(0.125) - R(1));
+    }
+    const real c[CSE_COEF_N(M_HI)] = CSE_COEF(M_HI);
+    return clenshaw(c, R(40) * r_rcp(v) - R(1.5)) * r_fsqrt(v);
+}
+CSE_D real cse_expint_e1_fast(real v) {
+    if (v <= R(1)) {
+        const real c[CSE_COEF_N(E_LO)] = CSE_COEF(E_LO);
+        return clenshaw(c, v + v - R(1)) - r_flog(v);
+    }
+    const real c[CSE_COEF_N(E_HI)] = CSE_COEF(E_HI);
+    const real rv = r_rcp(v);
+    return clenshaw(c, (rv + rv - R(1.0125)) * R(1.0 / 0.9875)) * r_fexp(-v) * rv;
+}

@@ -1,5 +1,5 @@
 // K3+K4: per-candidate gain (frame march) fused with the inverse real FFT and the weighted
-// overlap-add of librosa.istft.  One CTA per (utterance, grid point); one thread per bin.
+// overlap-add of librosa.istft.  One CTA per (utterance, grid point).
 //
 // Restates, after their STFT / noise_estimation calls:
 //   ALG 0  spectral_subtraction  Code/spectral_subtractor.py:37-62
@@ -9,12 +9,17 @@
 // and librosa.istft(S, hop_length, win_length=n_fft, window="hann", center=True, length=L).
 //
 // The decision-directed recursion is sequential over frames but independent per bin, so each
-// thread carries (previous gain, previous a-posteriori SNR, smoothed noise PSD) for its bin in
-// registers and marches F frames per iteration; the F gained spectra are turned into F packed
-// half-size inverse FFTs in shared memory (all threads busy), windowed, overlap-added into a
-// ring buffer, normalised by the running window sum-of-squares and streamed out, F*hop
-// finished samples per iteration.  Y / N reads and waveform writes are coalesced; the
-// spectra are prefetched into registers one iteration ahead.
+// thread carries (previous gain, previous a-posteriori SNR, smoothed noise PSD) for its BPT bins
+// in registers and marches F frames per iteration.  The F gained spectra are turned into F packed
+// half-size inverse FFTs in shared memory (F is chosen so that every thread has a radix-8
+// butterfly per pass), windowed, overlap-added into a ring buffer, normalised by the window
+// sum-of-squares and streamed out, F*hop finished samples per iteration.
+//
+// Thread layout: NTB = min(n_fft/2, 256) "bin" threads own bins tid, tid+NTB, ...; one extra warp
+// carries the Nyquist bin in its lane 0 so that no bin thread does double work in front of the
+// barrier; all NTB+32 threads share the FFT / overlap-add loops.  Y / N reads (coalesced, issued
+// for the NEXT iteration right after the gain phase so they fly during the FFT) and waveform
+// writes are coalesced.  Round-1 profile and the changes it drove: profiles/r01_*.md.
 #pragma once
 #include "cse_fft.cuh"
 #include "cse_special.cuh"
@@ -24,12 +29,13 @@ struct GainState { real g_prev, gam_prev, nsm; };
 template <int ALG>
 CSE_D real2 gain_apply(real2 Yv, real Nraw, bool first, GainState& st, const real* __restrict__ pv,
                        real eps, bool smooth) {
-    const real Pw = Yv.x * Yv.x + Yv.y * Yv.y;
+    const real Pw = r_fma(Yv.x, Yv.x, Yv.y * Yv.y);
     real Nt = r_max(Nraw, eps);
     if (ALG == 0) {
-        // Pc = max(P - alpha N, beta N); S = sqrt(Pc) * exp(j angle(Y))
-        const real Pc = r_max(Pw - pv[0] * Nt, pv[1] * Nt);
-        if (Pw > R(0)) { const real g = r_sqrt(Pc / Pw); return mk2(Yv.x * g, Yv.y * g); }
+        // Pc = max(P - alpha N, beta N); S = sqrt(Pc) * exp(j angle(Y)) = Y * sqrt(Pc / P)
+        const real Pc = r_max(r_fma(-pv[0], Nt, Pw), pv[1] * Nt);
+        if (Pw > R(1e-30)) { const real g = r_fsqrt(Pc * r_rcp(Pw)); return mk2(Yv.x * g, Yv.y * g); }
+        if (Pw > R(0)) { const real g = r_sqrt(Pc) / r_sqrt(Pw); return mk2(Yv.x * g, Yv.y * g); }
         return mk2(r_sqrt(Pc), R(0));
     }
     if (ALG >= 2 && smooth) {           // recursive smoothing of a time-varying noise PSD
@@ -38,30 +44,29 @@ CSE_D real2 gain_apply(real2 Yv, real Nraw, bool first, GainState& st, const rea
         st.nsm = Nt;
         Nt = r_max(Nt, eps);
     }
-    const real gam = r_max(Pw / Nt, eps);
+    const real gam = r_max(Pw * r_rcp(Nt), eps);
     const real direct = r_max(gam - R(1), R(0));
     const real alpha = pv[0];
+    const real rec = r_fma(alpha, st.g_prev * st.g_prev * st.gam_prev, (R(1) - alpha) * direct);
     real G;
     if (ALG == 1) {
-        real xi = first ? direct : r_fma(alpha, st.g_prev * st.g_prev * st.gam_prev, (R(1) - alpha) * direct);
-        xi = r_max(xi, R(1e-10));
-        G = r_clip(xi / (R(1) + xi), pv[1], R(1));
+        const real xi = r_max(first ? direct : rec, R(1e-10));
+        G = r_clip(xi * r_rcp(R(1) + xi), pv[1], R(1));
     } else {
-        const real ksi_min = pv[1];
-        real xi = first ? (gam - R(1)) : r_fma(alpha, st.g_prev * st.g_prev * st.gam_prev, (R(1) - alpha) * direct);
-        xi = r_max(xi, ksi_min);
+        const real xi = r_max(first ? (gam - R(1)) : rec, pv[1]);
+        const real r = r_rcp(R(1) + xi);
+        const real xr = xi * r;                                   // xi / (1 + xi)
         if (ALG == 2) {
-            const real v = r_clip(xi * gam / (R(1) + xi), eps, R(80));
-            const real A = R(0.88622692545275801365) * r_sqrt(v) / (gam + eps);
-            G = r_clip(A * cse_mmse_bessel_term(v), pv[2], pv[3]);
+            const real v = r_clip(xr * gam, eps, R(80));
+            const real A = R(0.88622692545275801365) * r_fsqrt(v) * r_rcp(gam + eps);
+            G = r_clip(A * cse_mmse_bessel_term_fast(v), pv[2], pv[3]);
         } else {
             const real gf = pv[2], q = pv[4], vmax = pv[5], lngf = pv[6];
-            const real v = r_clip(xi * gam / (R(1) + xi), R(1e-12), vmax);
-            const real opx = R(1) + xi;
-            const real lg = r_log(xi / opx) + R(0.5) * cse_expint_e1(v);          // ln(G_lsa)
-            const real lam = r_exp(v) / opx;
-            const real p = r_clip(R(1) / (R(1) + (R(1) - q) / r_fma(q, lam, eps)), R(0), R(1));
-            G = r_clip(r_exp(r_fma(p, lg - lngf, lngf)), gf, R(1));               // G_lsa^p gf^(1-p)
+            const real v = r_clip(xr * gam, R(1e-12), vmax);
+            const real lg = r_flog(xr) + R(0.5) * cse_expint_e1_fast(v);       // ln(G_lsa)
+            const real ql = r_fma(q, r_fexp(v) * r, eps);                       // q * Lambda + eps
+            const real p = r_clip(ql * r_rcp(ql + (R(1) - q)), R(0), R(1));     // 1 / (1 + (1-q)/ql)
+            G = r_clip(r_fexp(r_fma(p, lg - lngf, lngf)), gf, R(1));            // G_lsa^p gf^(1-p)
         }
     }
     st.g_prev = G;
@@ -79,18 +84,28 @@ struct EnhanceArgs {
     real eps;
 };
 
-template <int ALG, int LOG2N, int F>
-__global__ void __launch_bounds__(1 << (LOG2N - 1)) enhance_kernel(EnhanceArgs a) {
-    constexpr int NFFT = 1 << LOG2N, M = NFFT / 2, LOG2M = LOG2N - 1;
-    constexpr int XST = CSE_FFT_STRIDE(M) + 2;        // per-frame stride: M padded values + Nyquist slot
+template <int LOG2N> struct EnhanceCfg {
+    static constexpr int NFFT = 1 << LOG2N, M = NFFT / 2;
+    static constexpr int NTB = M < 256 ? M : 256;        // bin threads
+    static constexpr int BPT = M / NTB;                  // bins per bin thread
+    static constexpr int NT = NTB + 32;                  // + the Nyquist warp
+    static constexpr int F = (8 * NTB) / M;              // frames per iteration: F * M/8 butterflies == NTB
+    static constexpr int XST = CSE_FFT_STRIDE(M);        // per-frame stride; slot XST-1 holds the Nyquist bin
+};
+
+template <int ALG, int LOG2N>
+__global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, 3) enhance_kernel(EnhanceArgs a) {
+    typedef EnhanceCfg<LOG2N> C;
+    constexpr int NFFT = C::NFFT, M = C::M, LOG2M = LOG2N - 1, NTB = C::NTB, BPT = C::BPT, NT = C::NT, F = C::F;
+    constexpr int XST = C::XST, XNYQ = C::XST - 1;
     CSE_DYN_SMEM(smem_raw);
     real2* xs = reinterpret_cast<real2*>(smem_raw);                    // F * XST
     real* ring = reinterpret_cast<real*>(xs + F * XST);                // W
     const int hop = a.hop;
     const int W = NFFT + (F - 1) * hop;
-    real* ring2 = ring + W;                                            // window sum-of-squares ring
-    real* pv_s = ring2 + W;                                            // 8 params
-    const int tid = threadIdx.x;                                       // == bin index, blockDim.x == M
+    real* wsteady = ring + W;                                          // hop: steady-state window sum-of-squares
+    real* pv_s = wsteady + hop;                                        // 8 params
+    const int tid = threadIdx.x;
     const int item = a.item0 + blockIdx.x;
     const int u = item / a.n_params, c = item - u * a.n_params;
     const int nbp = cse_nbp(NFFT);
@@ -99,12 +114,17 @@ __global__ void __launch_bounds__(1 << (LOG2N - 1)) enhance_kernel(EnhanceArgs a
 
     if (tid < 8) {
         real v = (real)a.params[c].v[tid];
-        if (ALG == 2 && tid == 4) v = r_clip(v, R(0), R(0.9999));       // mmse.py:51
-        if (ALG == 3 && tid == 3) v = r_clip(v, R(0), R(0.9999));       // advanced_mmse.py:61
+        if (ALG == 2 && tid == 4) v = r_clip(v, R(0), R(0.9999));           // mmse.py:51
+        if (ALG == 3 && tid == 3) v = r_clip(v, R(0), R(0.9999));           // advanced_mmse.py:61
         if (ALG == 3 && tid == 4) v = r_clip(v, R(1e-3), R(1) - R(1e-3));   // advanced_mmse.py:72
         pv_s[tid] = v;
     }
-    for (int i = tid; i < 2 * W; i += M) ring[i] = R(0);
+    for (int i = tid; i < W; i += NT) ring[i] = R(0);
+    for (int r = tid; r < hop; r += NT) {
+        real s = R(0);
+        for (int n = r; n < NFFT; n += hop) s = r_fma(w[n], w[n], s);
+        wsteady[r] = s;
+    }
     __syncthreads();
     if (ALG == 3 && tid == 0) pv_s[6] = r_log(pv_s[2]);
     __syncthreads();
@@ -118,55 +138,64 @@ __global__ void __launch_bounds__(1 << (LOG2N - 1)) enhance_kernel(EnhanceArgs a
     const real* __restrict__ Nu = a.N + (size_t)u * (a.noise_tv ? (size_t)nf * nbp : (size_t)nbp);
     real* __restrict__ out = a.out + (size_t)blockIdx.x * L;
 
-    GainState st{R(1), R(1), R(0)}, stN{R(1), R(1), R(0)};     // stN: Nyquist bin, thread 0 only
-    const real n_static = a.noise_tv ? R(0) : Nu[tid];
-    const real n_static_ny = (!a.noise_tv && tid == 0) ? Nu[M] : R(0);
-
-    real2 ycur[F], ynxt[F];
-    real ncur[F], nnxt[F];
-    auto prefetch = [&](int t0, real2* yy, real* nn) {
+    // bins of this thread: bin threads own tid + i*NTB; lane 0 of the extra warp owns the Nyquist bin
+    const bool is_bin = tid < NTB, is_nyq = tid == NTB;
+    const int nb_mine = is_bin ? BPT : (is_nyq ? 1 : 0);
+    GainState st[BPT];
+    real nstat[BPT];
+    real2 yv[BPT][F];
+    real nv[BPT][F];
 #pragma unroll
-        for (int f = 0; f < F; ++f) {
-            const int t = t0 + f;
-            if (t < nf) {
-                yy[f] = Yu[(size_t)t * nbp + tid];
-                nn[f] = a.noise_tv ? Nu[(size_t)t * nbp + tid] : n_static;
-            } else { yy[f] = mk2(R(0), R(0)); nn[f] = R(1); }
+    for (int i = 0; i < BPT; ++i) {
+        st[i].g_prev = R(1); st[i].gam_prev = R(1); st[i].nsm = R(0);
+        const int b = is_bin ? tid + i * NTB : M;
+        nstat[i] = (!a.noise_tv && i < nb_mine) ? Nu[b] : R(1);
+    }
+    auto fetch = [&](int t0) {
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) {
+            const int b = is_bin ? tid + i * NTB : M;
+#pragma unroll
+            for (int f = 0; f < F; ++f) {
+                const int t = t0 + f;
+                if (i < nb_mine && t < nf) {
+                    yv[i][f] = Yu[(size_t)t * nbp + b];
+                    nv[i][f] = a.noise_tv ? Nu[(size_t)t * nbp + b] : nstat[i];
+                } else { yv[i][f] = mk2(R(0), R(0)); nv[i][f] = R(1); }
+            }
         }
     };
-    prefetch(0, ycur, ncur);
+    fetch(0);
 
     const int total_pos = L + M;             // padded positions [0, L + M) must be emitted
     int ring_base = 0;                       // ring slot of padded position t0 * hop
-    const real scale = R(1) / (real)NFFT;    // irfft normalisation (1/2 of the split and 1/M of the FFT)
+    const real scale = R(1) / (real)NFFT;    // irfft normalisation (1/2 of the split, 1/M of the FFT)
+    const bool vec2 = (L & 1) == 0;          // waveform rows 8-byte aligned -> paired stores
 
     for (int t0 = 0; t0 * hop < total_pos; t0 += F) {
         const bool any = t0 < nf;
         if (any) {
 #pragma unroll
-            for (int f = 0; f < F; ++f) {
-                const int t = t0 + f;
-                if (t < nf) {
-                    xs[f * XST + SIDX(tid)] = gain_apply<ALG>(ycur[f], ncur[f], t == 0, st, pv, a.eps, smooth);
-                    if (tid == 0) {
-                        const real2 yn = Yu[(size_t)t * nbp + M];
-                        const real nn = a.noise_tv ? Nu[(size_t)t * nbp + M] : n_static_ny;
-                        xs[f * XST + CSE_FFT_STRIDE(M)] = gain_apply<ALG>(yn, nn, t == 0, stN, pv, a.eps, smooth);
+            for (int i = 0; i < BPT; ++i) {
+                if (i < nb_mine) {
+                    const int slot = is_bin ? SIDX(tid + i * NTB) : XNYQ;
+#pragma unroll
+                    for (int f = 0; f < F; ++f) {
+                        const int t = t0 + f;
+                        xs[f * XST + slot] = (t < nf) ? gain_apply<ALG>(yv[i][f], nv[i][f], t == 0, st[i], pv, a.eps, smooth)
+                                                      : mk2(R(0), R(0));
                     }
-                } else {
-                    xs[f * XST + SIDX(tid)] = mk2(R(0), R(0));
-                    if (tid == 0) xs[f * XST + CSE_FFT_STRIDE(M)] = mk2(R(0), R(0));
                 }
             }
-            prefetch(t0 + F, ynxt, nnxt);
+            fetch(t0 + F);                   // next iteration's spectra fly during the FFT
             __syncthreads();
             // pre-split (in place): Z[k] = E + iO, Z[M-k] = conj(E) + i conj(O);
             // E = X[k] + conj X[M-k], O = (X[k] - conj X[M-k]) W_N^-k   (scale 1/2 folded into `scale`)
-            for (int idx = tid; idx < F * (M / 2 + 1); idx += M) {
+            for (int idx = tid; idx < F * (M / 2 + 1); idx += NT) {
                 const int f = idx / (M / 2 + 1), k = idx - f * (M / 2 + 1);
                 real2* xf = xs + f * XST;
                 if (k == 0) {
-                    const real x0 = xf[0].x, xm = xf[CSE_FFT_STRIDE(M)].x;
+                    const real x0 = xf[0].x, xm = xf[XNYQ].x;
                     xf[0] = mk2(x0 + xm, x0 - xm);
                 } else if (k == M / 2) {
                     const real2 x = xf[SIDX(k)];
@@ -181,49 +210,68 @@ __global__ void __launch_bounds__(1 << (LOG2N - 1)) enhance_kernel(EnhanceArgs a
                 }
             }
             __syncthreads();
-            fft_dif<LOG2M, true>(xs, F, XST, a.T->tw, tid, M);
+            fft_dif<LOG2M, true>(xs, F, XST, a.T->tw, tid, NT);
         }
-        // overlap-add the F windowed frames, emit the F*hop positions no later frame touches
+        // overlap-add the F windowed frames two samples at a time (sample pair 2m,2m+1 of a frame
+        // is one complex FFT output), emit the F*hop positions no later frame touches
         const int p_begin = t0 * hop;
         const int emit_end = p_begin + F * hop;
-        for (int j = tid; j < W; j += M) {
-            const int p = p_begin + j;
+        for (int jj = tid; jj < W / 2; jj += NT) {
+            const int j = 2 * jj, p = p_begin + j;
             int slot = ring_base + j;
             if (slot >= W) slot -= W;
-            real acc = ring[slot], acc2 = ring2[slot];
+            real2 acc = *reinterpret_cast<real2*>(ring + slot);
             if (any) {
 #pragma unroll
                 for (int f = 0; f < F; ++f) {
-                    const int n = j - f * hop;               // sample index inside frame t0+f
+                    const int n = j - f * hop;               // even sample index inside frame t0+f
                     if (n >= 0 && n < NFFT && t0 + f < nf) {
                         const real2 zz = xs[f * XST + SIDX(brev_n(n >> 1, LOG2M))];
-                        const real wv = w[n];
-                        acc = r_fma((n & 1) ? zz.y : zz.x, wv * scale, acc);
-                        acc2 = r_fma(wv, wv, acc2);
+                        acc.x = r_fma(zz.x, w[n], acc.x);
+                        acc.y = r_fma(zz.y, w[n + 1], acc.y);
                     }
                 }
             }
             if (p < emit_end) {
                 const int i = p - M;
-                if (i >= 0 && i < L) {
+                if (i >= -1 && i < L) {
+                    // window sum-of-squares of the frames covering p and p+1 (librosa window_sumsquare)
+                    real ws[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int pe = p + e;
+                        const int tmax = pe / hop, r = pe - tmax * hop;
+                        const int kmax = (NFFT - 1 - r) / hop;          // frames tmax-k, k <= kmax, cover pe
+                        if (tmax - kmax >= 0 && tmax < nf) ws[e] = wsteady[r];
+                        else {
+                            real s = R(0);
+                            for (int k = 0; k <= kmax; ++k) {
+                                const int t = tmax - k;
+                                if (t >= 0 && t < nf) s = r_fma(w[r + k * hop], w[r + k * hop], s);
+                            }
+                            ws[e] = s;
+                        }
+                    }
 #ifdef CSE_FP64
                     const real tiny = 2.2250738585072014e-308;
 #else
                     const real tiny = 1.17549435e-38f;
 #endif
-                    out[i] = acc2 > tiny ? acc / acc2 : acc;
+                    const real o0 = ws[0] > tiny ? acc.x * scale / ws[0] : acc.x * scale;
+                    const real o1 = ws[1] > tiny ? acc.y * scale / ws[1] : acc.y * scale;
+                    if (vec2 && i >= 0 && i + 1 < L) *reinterpret_cast<real2*>(out + i) = mk2(o0, o1);
+                    else {
+                        if (i >= 0) out[i] = o0;
+                        if (i + 1 < L) out[i + 1] = o1;
+                    }
                 }
-                ring[slot] = R(0);
-                ring2[slot] = R(0);
+                *reinterpret_cast<real2*>(ring + slot) = mk2(R(0), R(0));
             } else {
-                ring[slot] = acc;
-                ring2[slot] = acc2;
+                *reinterpret_cast<real2*>(ring + slot) = acc;
             }
         }
         ring_base += F * hop;
         while (ring_base >= W) ring_base -= W;
-#pragma unroll
-        for (int f = 0; f < F; ++f) { ycur[f] = ynxt[f]; ncur[f] = nnxt[f]; }
         __syncthreads();
     }
 }
