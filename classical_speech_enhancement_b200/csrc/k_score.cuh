@@ -23,6 +23,17 @@
 // correlation against cached clean-side statistics.
 #pragma once
 #include "cse_fft.cuh"
+#include "cse_resampler_taps.h"
+
+// Resampler taps as compile-time-indexed constant-bank operands: with the row loop fully
+// unrolled every tap is a c[bank][offset] operand of its FFMA (no load instruction), and the
+// structurally zero taps (each output phase only reaches 116-117 of the 136 tile rows) are
+// skipped at compile time.
+#ifdef CSE_EMU
+static const real c_rs[CSE_RS_ROWS * 8] = {CSE_RS_TAP_VALUES};
+#else
+__device__ __constant__ real c_rs[CSE_RS_ROWS * 8] = {CSE_RS_TAP_VALUES};
+#endif
 
 #define CSE_SR 16000
 #define CSE_CORR_LOG2P 13
@@ -50,7 +61,7 @@ struct CleanHeader {
 
 struct ScoreGeom {
     int L, Nc, maxlag, nblocks, npairs, n10, nfr, nfrm, jmax;
-    size_t off_kept, off_xtob, off_seg, off_rsum, off_q, bytes;
+    size_t off_kept, off_need, off_xtob, off_seg, off_rsum, off_q, bytes;
 };
 
 static inline ScoreGeom score_geom(int L) {
@@ -67,6 +78,7 @@ static inline ScoreGeom score_geom(int L) {
     auto up = [](size_t x) { return (x + 63) & ~(size_t)63; };
     size_t o = up(sizeof(CleanHeader));
     g.off_kept = o; o = up(o + sizeof(int) * (size_t)(g.nfr + 1));
+    g.off_need = o; o = up(o + (size_t)((g.n10 + 4) / 5 + 8));       // one byte per resampler group of 5 outputs
     g.off_xtob = o; o = up(o + sizeof(real) * (size_t)CSE_NBANDS * (g.nfrm + 1));
     g.off_seg = o; o = up(o + sizeof(real) * (size_t)3 * CSE_NBANDS * (g.jmax + 1));
     g.off_rsum = o; o = up(o + sizeof(real) * (size_t)(2 * CSE_MAXLAG + 1));
@@ -136,7 +148,7 @@ struct ScoreArgs {
 
 // ---------------------------------------------------------------- alignment
 template <bool CLEAN>
-__global__ void __launch_bounds__(512) align_kernel(ScoreArgs a) {
+__global__ void __launch_bounds__(512, 2) align_kernel(ScoreArgs a) {
     constexpr int P = CSE_CORR_P, NT = 512, PER = P / NT, M = CSE_MAXLAG, B = CSE_CORR_B;
     CSE_DYN_SMEM(smem_raw);
     real2* z = reinterpret_cast<real2*>(smem_raw);                              // CSE_FFT_STRIDE(P)
@@ -258,25 +270,39 @@ __global__ void __launch_bounds__(512) align_kernel(ScoreArgs a) {
 
 // ---------------------------------------------------------------- resampler
 // One pass: outputs y10[5a + p], a in [a0, a0 + A), from the de-interleaved tile xs[c][ap]
-// (c = sample index mod 8, AP = A + 17 columns).  TA = accumulator type.
-template <class TA, class TG, class TO>
+// (c = sample index mod 8, AP = A + 17 columns).  TA = accumulator type.  CONSTTAPS: taps from
+// the constant bank (candidate path); otherwise from the table G (double-precision clean path).
+template <class TA, class TG, class TO, bool CONSTTAPS>
 CSE_D void resample_pass(const real* __restrict__ sig, int L, int lag, bool finalize, const TG* __restrict__ G /*[136][8]*/,
-                         TA* xs, int a0, TO* __restrict__ y10, int n10, int tid, int nth) {
+                         TA* xs, int a0, TO* __restrict__ y10, int n10, int tid, int nth,
+                         const unsigned char* __restrict__ need = nullptr) {
     constexpr int A = CSE_RS_A, AP = A + 17;
     const int j0 = 8 * a0 - 64;
     for (int jj = tid; jj < 8 * AP; jj += nth) xs[(jj & 7) * AP + (jj >> 3)] = (TA)xhat(sig, j0 + jj, lag, L, finalize);
     __syncthreads();
     for (int al = tid; al < A; al += nth) {
         const int a = a0 + al;
-        if (5 * a < n10) {
+        if (5 * a < n10 && (need == nullptr || need[a])) {
             TA acc[5] = {0, 0, 0, 0, 0};
-            for (int o = 0; o < 17; ++o) {
+            if (CONSTTAPS) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const TA x = xs[c * AP + al + o];
-                    const TG* g = G + (size_t)(8 * o + c) * 8;
+                for (int jj = 6; jj <= 128; ++jj) {                 // rows 0-5 and 129-135 hold no tap
+                    const TA x = xs[(jj & 7) * AP + al + (jj >> 3)];
 #pragma unroll
-                    for (int p = 0; p < 5; ++p) acc[p] += x * (TA)g[p];
+                    for (int p = 0; p < 5; ++p) {
+                        const int idx = 8 * p + 610 - 5 * jj;        // compile-time after unrolling
+                        if (idx >= 0 && idx <= 580) acc[p] += x * (TA)c_rs[jj * 8 + p];
+                    }
+                }
+            } else {
+                for (int o = 0; o < 17; ++o) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const TA x = xs[c * AP + al + o];
+                        const TG* g = G + (size_t)(8 * o + c) * 8;
+#pragma unroll
+                        for (int p = 0; p < 5; ++p) acc[p] += x * (TA)g[p];
+                    }
                 }
             }
 #pragma unroll
@@ -301,7 +327,7 @@ __global__ void __launch_bounds__(256) clean_vad_kernel(ScoreArgs a, double* __r
     int* kept = reinterpret_cast<int*>(rec + g.off_kept);
     const int na = (g.n10 + 4) / 5;
     for (int a0 = 0; a0 < na; a0 += CSE_RS_A)
-        resample_pass<double, double, double>(sig, g.L, 0, false, &a.T->rs_d[0][0], xs, a0, yd, g.n10, tid, 256);
+        resample_pass<double, double, double, false>(sig, g.L, 0, false, &a.T->rs_d[0][0], xs, a0, yd, g.n10, tid, 256);
     __threadfence_block();
     __syncthreads();
     // frame energies in dB: 20 log10(||w * frame|| + EPS)
@@ -331,6 +357,23 @@ __global__ void __launch_bounds__(256) clean_vad_kernel(ScoreArgs a, double* __r
         hdr->K = K;
         hdr->J = (K - 1 >= CSE_NSEG) ? (K - 1) - CSE_NSEG + 1 : 0;
     }
+    __threadfence_block();
+    __syncthreads();
+    // resampler groups a (outputs 5a..5a+4) that land in a kept frame's samples [128k, 128k + 256)
+    {
+        unsigned char* need = rec + g.off_need;
+        const int K = hdr->K;
+        for (int a5 = tid; a5 < na; a5 += 256) {
+            const int lo = 5 * a5, hi = lo + 4;           // output sample range of this group
+            // frames f with 128f <= hi and 128f + 255 >= lo
+            int f0 = (lo - 255 + 127) / 128;
+            if (f0 < 0) f0 = 0;
+            const int f1 = hi / 128;
+            unsigned char nd = 0;
+            for (int j = 0; j < K && !nd; ++j) { const int f = kept[j]; if (f >= f0 && f <= f1) nd = 1; else if (f > f1) break; }
+            need[a5] = nd;
+        }
+    }
 }
 
 // ---------------------------------------------------------------- STOI + SNR
@@ -348,11 +391,11 @@ __global__ void __launch_bounds__(256) stoi_kernel(ScoreArgs a, const double* __
     const int* __restrict__ kept = reinterpret_cast<const int*>(rec + g.off_kept);
     real* xtob_c = reinterpret_cast<real*>(rec + g.off_xtob);
     real* seg_c = reinterpret_cast<real*>(rec + g.off_seg);
+    const unsigned char* __restrict__ need = rec + g.off_need;   // resampler groups that feed a kept frame
     const int K = hdr->K, Kf = K > 0 ? K - 1 : 0, J = hdr->J;
 
     double* scratch = reinterpret_cast<double*>(smem_raw);                    // 40 doubles
-    real* gtab = reinterpret_cast<real*>(scratch + 40);                       // 136 * 8
-    real2* fbuf = reinterpret_cast<real2*>(gtab + CSE_RS_GROWS * 8);          // T * BST (aliases the resampler tile)
+    real2* fbuf = reinterpret_cast<real2*>(scratch + 40);                     // T * BST (aliases the resampler tile)
     real* pw = reinterpret_cast<real*>(fbuf + T * BST);                       // T * NK
     real* ytob = pw + T * NK;                                                 // 15 * Kf
     real* xtob = ytob + CSE_NBANDS * (g.nfrm + 1);                            // 15 * Kf (MODE 0)
@@ -382,12 +425,11 @@ __global__ void __launch_bounds__(256) stoi_kernel(ScoreArgs a, const double* __
             return;
         }
         const double pnoise = block_sum<double>((double)pn, scratch);
-        for (int i = tid; i < CSE_RS_GROWS * 8; i += NT) gtab[i] = (&a.T->rs[0][0])[i];
         for (int i = tid; i < CSE_NBANDS * Kf; i += NT) xtob[i] = xtob_c[i];
         __syncthreads();
         const int na = (g.n10 + 4) / 5;
         for (int a0 = 0; a0 < na; a0 += CSE_RS_A)
-            resample_pass<real, real, real>(sig, g.L, lag, fin, gtab, xs, a0, y10, g.n10, tid, NT);
+            resample_pass<real, real, real, true>(sig, g.L, lag, fin, (const real*)nullptr, xs, a0, y10, g.n10, tid, NT, need);
         __threadfence_block();
         __syncthreads();
         if (tid == 0) {
