@@ -224,7 +224,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--utts", type=int, default=824)
     ap.add_argument("--length", type=int, default=48000)
-    ap.add_argument("--chunk", type=int, default=1184)
+    ap.add_argument("--chunk", type=int, default=4736)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

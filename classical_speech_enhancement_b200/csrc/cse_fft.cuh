@@ -50,14 +50,15 @@ template <int m, bool CONJ> CSE_D real2 rotf(real2 d) { return CONJ ? rot8c<m>(d
 
 // One pass of RL fused DIF stages (CONJ: conjugated twiddles = inverse transform).  `h` = half size of the first fused stage,
 // q = h >> (RL-1) = smallest butterfly distance of the pass.
-template <int LOG2N, int RL, bool CONJ>
-CSE_D void dif_pass(real2* s, int nbatch, int bstride, int h, const real2* __restrict__ tw, int tid, int nth) {
+template <int LOG2N, int RL, bool CONJ, int H>
+CSE_D void dif_pass(real2* s, int nbatch, int bstride, const real2* __restrict__ tw, int tid, int nth) {
     constexpr int N = 1 << LOG2N;
     constexpr int NB = 1 << RL;               // elements per butterfly
-    const int q = h >> (RL - 1);
-    const int per = N / NB;
+    constexpr int h = H;
+    constexpr int q = h >> (RL - 1);
+    constexpr int per = N / NB;
     const int total = nbatch * per;
-    const int twstep = (CSE_TW_N / 2) / h;    // W_{2h}^p = W_T^{p * T/(2h)}
+    constexpr int twstep = (CSE_TW_N / 2) / h;    // W_{2h}^p = W_T^{p * T/(2h)}
     for (int idx = tid; idx < total; idx += nth) {
         const int b = idx / per, r = idx - b * per;
         const int j = r & (q - 1), grp = r / q;
@@ -97,13 +98,14 @@ CSE_D void dif_pass(real2* s, int nbatch, int bstride, int h, const real2* __res
 }
 
 // One pass of RL fused DIT stages; q = half size of the FIRST (smallest) fused stage.
-template <int LOG2N, int RL, bool CONJ>
-CSE_D void dit_pass(real2* s, int nbatch, int bstride, int q, const real2* __restrict__ tw, int tid, int nth) {
+template <int LOG2N, int RL, bool CONJ, int Q>
+CSE_D void dit_pass(real2* s, int nbatch, int bstride, const real2* __restrict__ tw, int tid, int nth) {
     constexpr int N = 1 << LOG2N;
     constexpr int NB = 1 << RL;
-    const int per = N / NB;
+    constexpr int q = Q;
+    constexpr int per = N / NB;
     const int total = nbatch * per;
-    const int twq = (CSE_TW_N / 2) / q;       // W_{2q}^p = W_T^{p * T/(2q)}
+    constexpr int twq = (CSE_TW_N / 2) / q;       // W_{2q}^p = W_T^{p * T/(2q)}
     for (int idx = tid; idx < total; idx += nth) {
         const int b = idx / per, r = idx - b * per;
         const int j = r & (q - 1), grp = r / q;
@@ -144,26 +146,31 @@ CSE_D void dit_pass(real2* s, int nbatch, int bstride, int q, const real2* __res
 }
 
 // Decimation-in-frequency transform, natural-order in -> bit-reversed out.  INV=false: forward
-// (e^-j); INV=true: unnormalised inverse (e^+j).  Ends with a __syncthreads().
+// (e^-j); INV=true: unnormalised inverse (e^+j).  Ends with a __syncthreads().  Stage sizes are
+// template constants so that all index arithmetic folds to shifts and masks.
 template <int LOG2N, bool INV>
 CSE_D void fft_dif(real2* s, int nbatch, int bstride, const real2* __restrict__ tw, int tid, int nth) {
-    constexpr int REM = LOG2N % 3;
-    int h = 1 << (LOG2N - 1);
-    if (REM == 1) { dif_pass<LOG2N, 1, INV>(s, nbatch, bstride, h, tw, tid, nth); __syncthreads(); h >>= 1; }
-    if (REM == 2) { dif_pass<LOG2N, 2, INV>(s, nbatch, bstride, h, tw, tid, nth); __syncthreads(); h >>= 2; }
-#pragma unroll
-    for (int p = 0; p < LOG2N / 3; ++p) { dif_pass<LOG2N, 3, INV>(s, nbatch, bstride, h, tw, tid, nth); __syncthreads(); h >>= 3; }
+    constexpr int REM = LOG2N % 3, NP = LOG2N / 3;
+    constexpr int H0 = 1 << (LOG2N - 1), H1 = H0 >> REM;
+    if constexpr (REM == 1) { dif_pass<LOG2N, 1, INV, H0>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (REM == 2) { dif_pass<LOG2N, 2, INV, H0>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 1) { dif_pass<LOG2N, 3, INV, H1>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 2) { dif_pass<LOG2N, 3, INV, (H1 >> 3)>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 3) { dif_pass<LOG2N, 3, INV, (H1 >> 6)>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 4) { dif_pass<LOG2N, 3, INV, (H1 >> 9)>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
 }
 
 // Decimation-in-time transform, bit-reversed in -> natural-order out.  Ends with a __syncthreads().
 template <int LOG2N, bool INV>
 CSE_D void fft_dit(real2* s, int nbatch, int bstride, const real2* __restrict__ tw, int tid, int nth) {
-    constexpr int REM = LOG2N % 3;
-    int q = 1;
-#pragma unroll
-    for (int p = 0; p < LOG2N / 3; ++p) { dit_pass<LOG2N, 3, INV>(s, nbatch, bstride, q, tw, tid, nth); __syncthreads(); q <<= 3; }
-    if (REM == 2) { dit_pass<LOG2N, 2, INV>(s, nbatch, bstride, q, tw, tid, nth); __syncthreads(); }
-    if (REM == 1) { dit_pass<LOG2N, 1, INV>(s, nbatch, bstride, q, tw, tid, nth); __syncthreads(); }
+    constexpr int REM = LOG2N % 3, NP = LOG2N / 3;
+    if constexpr (NP >= 1) { dit_pass<LOG2N, 3, INV, 1>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 2) { dit_pass<LOG2N, 3, INV, 8>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 3) { dit_pass<LOG2N, 3, INV, 64>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 4) { dit_pass<LOG2N, 3, INV, 512>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    constexpr int QR = 1 << (3 * NP);
+    if constexpr (REM == 2) { dit_pass<LOG2N, 2, INV, QR>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (REM == 1) { dit_pass<LOG2N, 1, INV, QR>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
 }
 
 CSE_D int brev_n(int k, int log2n) { return (int)(__brev((unsigned)k) >> (32 - log2n)); }

@@ -15,9 +15,10 @@
 // butterfly per pass), windowed, overlap-added into a ring buffer, normalised by the window
 // sum-of-squares and streamed out, F*hop finished samples per iteration.
 //
-// Thread layout: NTB = min(n_fft/2, 256) "bin" threads own bins tid, tid+NTB, ...; one extra warp
-// carries the Nyquist bin in its lane 0 so that no bin thread does double work in front of the
-// barrier; all NTB+32 threads share the FFT / overlap-add loops.  Y / N reads (coalesced, issued
+// Thread layout: NTB = min(n_fft/4, 256) "pair" threads own the bin pairs (s, M-s), M = n_fft/2
+// (slot 0 is DC + Nyquist); one extra warp carries the self-paired bin M/2 in its lane 0 so that
+// no thread does extra work in front of the barrier; all NTB+32 threads share the FFT /
+// overlap-add loops.  Y / N reads (coalesced, issued
 // for the NEXT iteration right after the gain phase so they fly during the FFT) and waveform
 // writes are coalesced.  Round-1 profile and the changes it drove: profiles/r01_*.md.
 #pragma once
@@ -86,18 +87,24 @@ struct EnhanceArgs {
 
 template <int LOG2N> struct EnhanceCfg {
     static constexpr int NFFT = 1 << LOG2N, M = NFFT / 2;
-    static constexpr int NTB = M < 256 ? M : 256;        // bin threads
-    static constexpr int BPT = M / NTB;                  // bins per bin thread
-    static constexpr int NT = NTB + 32;                  // + the Nyquist warp
-    static constexpr int F = (8 * NTB) / M;              // frames per iteration: F * M/8 butterflies == NTB
-    static constexpr int XST = CSE_FFT_STRIDE(M);        // per-frame stride; slot XST-1 holds the Nyquist bin
+    static constexpr int NPAIR = M / 2;                      // pair slots s: bins (s, M-s); slot 0 = (DC, Nyquist)
+    static constexpr int NTB = NPAIR < 256 ? NPAIR : 256;    // pair threads
+    static constexpr int PPT = NPAIR / NTB;                  // pair slots per pair thread
+    static constexpr int NT = NTB + 32;                      // + one warp whose lane 0 owns the self-paired bin M/2
+    static constexpr int F = (8 * NTB) / M;                  // frames per iteration: F * M/8 butterflies == NTB
+    static constexpr int XST = CSE_FFT_STRIDE(M);            // per-frame stride of the packed half-size spectra
 };
 
+// One CTA per (utterance, grid point).  Each pair thread owns the bins (s, M-s) of its PPT pair
+// slots: the packed half-size inverse-FFT input Z[s] = E + iO, Z[M-s] = conj(E) + i conj(O)
+// (E = X[s] + conj X[M-s], O = (X[s] - conj X[M-s]) W_N^-s) needs exactly those two gained bins,
+// so it is formed in registers and written straight into the FFT buffer - no separate split
+// pass, no exchange through shared memory.
 template <int ALG, int LOG2N>
-__global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, 3) enhance_kernel(EnhanceArgs a) {
+__global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (LOG2N >= 10 ? 3 : 4)) enhance_kernel(EnhanceArgs a) {
     typedef EnhanceCfg<LOG2N> C;
-    constexpr int NFFT = C::NFFT, M = C::M, LOG2M = LOG2N - 1, NTB = C::NTB, BPT = C::BPT, NT = C::NT, F = C::F;
-    constexpr int XST = C::XST, XNYQ = C::XST - 1;
+    constexpr int NFFT = C::NFFT, M = C::M, LOG2M = LOG2N - 1, NTB = C::NTB, PPT = C::PPT, NT = C::NT, F = C::F;
+    constexpr int XST = C::XST;
     CSE_DYN_SMEM(smem_raw);
     real2* xs = reinterpret_cast<real2*>(smem_raw);                    // F * XST
     real* ring = reinterpret_cast<real*>(xs + F * XST);                // W
@@ -138,30 +145,37 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, 3) enhance_kernel(Enhan
     const real* __restrict__ Nu = a.N + (size_t)u * (a.noise_tv ? (size_t)nf * nbp : (size_t)nbp);
     real* __restrict__ out = a.out + (size_t)blockIdx.x * L;
 
-    // bins of this thread: bin threads own tid + i*NTB; lane 0 of the extra warp owns the Nyquist bin
-    const bool is_bin = tid < NTB, is_nyq = tid == NTB;
-    const int nb_mine = is_bin ? BPT : (is_nyq ? 1 : 0);
-    GainState st[BPT];
-    real nstat[BPT];
-    real2 yv[BPT][F];
-    real nv[BPT][F];
+    const bool is_pair = tid < NTB, is_mid = tid == NTB;       // lane 0 of the extra warp: bin M/2
+    const int n_slots = is_pair ? PPT : (is_mid ? 1 : 0);
+    GainState st[PPT][2];
+    real nstat[PPT][2];
+    real2 twc[PPT];                                           // W_N^s of each pair slot
+    real2 yv[PPT][2][F];
+    real nv[PPT][2][F];
+    // bins (ka, kb) of slot i: pair thread -> (s, M - s) with s = tid + i*NTB (slot 0: (0, M)); mid lane -> (M/2, -)
+    auto bin_a = [&](int i) { return is_pair ? tid + i * NTB : M / 2; };
+    auto bin_b = [&](int i) { return M - (tid + i * NTB); };
 #pragma unroll
-    for (int i = 0; i < BPT; ++i) {
-        st[i].g_prev = R(1); st[i].gam_prev = R(1); st[i].nsm = R(0);
-        const int b = is_bin ? tid + i * NTB : M;
-        nstat[i] = (!a.noise_tv && i < nb_mine) ? Nu[b] : R(1);
+    for (int i = 0; i < PPT; ++i) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) { st[i][e].g_prev = R(1); st[i][e].gam_prev = R(1); st[i][e].nsm = R(0); }
+        nstat[i][0] = (!a.noise_tv && i < n_slots) ? Nu[bin_a(i)] : R(1);
+        nstat[i][1] = (!a.noise_tv && is_pair) ? Nu[bin_b(i)] : R(1);
+        twc[i] = tw_load(a.T->tw, (is_pair ? tid + i * NTB : 0) * (CSE_TW_N / NFFT));
     }
     auto fetch = [&](int t0) {
 #pragma unroll
-        for (int i = 0; i < BPT; ++i) {
-            const int b = is_bin ? tid + i * NTB : M;
+        for (int i = 0; i < PPT; ++i) {
+            const int ka = bin_a(i), kb = bin_b(i);
 #pragma unroll
             for (int f = 0; f < F; ++f) {
                 const int t = t0 + f;
-                if (i < nb_mine && t < nf) {
-                    yv[i][f] = Yu[(size_t)t * nbp + b];
-                    nv[i][f] = a.noise_tv ? Nu[(size_t)t * nbp + b] : nstat[i];
-                } else { yv[i][f] = mk2(R(0), R(0)); nv[i][f] = R(1); }
+                const bool on = i < n_slots && t < nf;
+                yv[i][0][f] = on ? Yu[(size_t)t * nbp + ka] : mk2(R(0), R(0));
+                nv[i][0][f] = on ? (a.noise_tv ? Nu[(size_t)t * nbp + ka] : nstat[i][0]) : R(1);
+                const bool onb = on && is_pair;
+                yv[i][1][f] = onb ? Yu[(size_t)t * nbp + kb] : mk2(R(0), R(0));
+                nv[i][1][f] = onb ? (a.noise_tv ? Nu[(size_t)t * nbp + kb] : nstat[i][1]) : R(1);
             }
         }
     };
@@ -176,39 +190,31 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, 3) enhance_kernel(Enhan
         const bool any = t0 < nf;
         if (any) {
 #pragma unroll
-            for (int i = 0; i < BPT; ++i) {
-                if (i < nb_mine) {
-                    const int slot = is_bin ? SIDX(tid + i * NTB) : XNYQ;
+            for (int i = 0; i < PPT; ++i) {
+                if (i < n_slots) {
+                    const int s = tid + i * NTB;
 #pragma unroll
                     for (int f = 0; f < F; ++f) {
                         const int t = t0 + f;
-                        xs[f * XST + slot] = (t < nf) ? gain_apply<ALG>(yv[i][f], nv[i][f], t == 0, st[i], pv, a.eps, smooth)
-                                                      : mk2(R(0), R(0));
+                        real2* xf = xs + f * XST;
+                        if (t >= nf) {
+                            if (is_pair) { xf[SIDX(s)] = mk2(R(0), R(0)); if (s > 0) xf[SIDX(M - s)] = mk2(R(0), R(0)); }
+                            else xf[SIDX(M / 2)] = mk2(R(0), R(0));
+                            continue;
+                        }
+                        const real2 xa = gain_apply<ALG>(yv[i][0][f], nv[i][0][f], t == 0, st[i][0], pv, a.eps, smooth);
+                        if (!is_pair) { xf[SIDX(M / 2)] = mk2(R(2) * xa.x, R(-2) * xa.y); continue; }   // 2 conj X[M/2]
+                        const real2 xb = gain_apply<ALG>(yv[i][1][f], nv[i][1][f], t == 0, st[i][1], pv, a.eps, smooth);
+                        if (s == 0) { xf[0] = mk2(xa.x + xb.x, xa.x - xb.x); continue; }                // DC, Nyquist (real)
+                        const real2 E = mk2(xa.x + xb.x, xa.y - xb.y);
+                        const real2 D = mk2(xa.x - xb.x, xa.y + xb.y);
+                        const real2 O = cmulc(D, twc[i]);                      // D * W_N^-s
+                        xf[SIDX(s)] = mk2(E.x - O.y, E.y + O.x);               // E + iO
+                        xf[SIDX(M - s)] = mk2(E.x + O.y, O.x - E.y);           // conj(E) + i conj(O)
                     }
                 }
             }
             fetch(t0 + F);                   // next iteration's spectra fly during the FFT
-            __syncthreads();
-            // pre-split (in place): Z[k] = E + iO, Z[M-k] = conj(E) + i conj(O);
-            // E = X[k] + conj X[M-k], O = (X[k] - conj X[M-k]) W_N^-k   (scale 1/2 folded into `scale`)
-            for (int idx = tid; idx < F * (M / 2 + 1); idx += NT) {
-                const int f = idx / (M / 2 + 1), k = idx - f * (M / 2 + 1);
-                real2* xf = xs + f * XST;
-                if (k == 0) {
-                    const real x0 = xf[0].x, xm = xf[XNYQ].x;
-                    xf[0] = mk2(x0 + xm, x0 - xm);
-                } else if (k == M / 2) {
-                    const real2 x = xf[SIDX(k)];
-                    xf[SIDX(k)] = mk2(R(2) * x.x, R(-2) * x.y);
-                } else {
-                    const real2 xa = xf[SIDX(k)], xb = xf[SIDX(M - k)];
-                    const real2 E = mk2(xa.x + xb.x, xa.y - xb.y);
-                    const real2 D = mk2(xa.x - xb.x, xa.y + xb.y);
-                    const real2 O = cmulc(D, tw_load(a.T->tw, k * (CSE_TW_N / NFFT)));   // D * W_N^-k
-                    xf[SIDX(k)] = mk2(E.x - O.y, E.y + O.x);            // E + iO
-                    xf[SIDX(M - k)] = mk2(E.x + O.y, O.x - E.y);        // conj(E) + i conj(O)
-                }
-            }
             __syncthreads();
             fft_dif<LOG2M, true>(xs, F, XST, a.T->tw, tid, NT);
         }

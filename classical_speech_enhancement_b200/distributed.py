@@ -55,7 +55,7 @@ def gather_scores(local, n_utts, device=None):
     return out
 
 
-def sweep_sharded(clean, noisy, grids=None, select=True, chunk_items=1184, device=None, engine_kwargs=None):
+def sweep_sharded(clean, noisy, grids=None, select=True, chunk_items=4736, device=None, engine_kwargs=None):
     """Each rank sweeps its block of utterances; every rank returns the full gathered tables.
     ``clean`` / ``noisy`` are the full host arrays [U, L] (each rank slices its block)."""
     import torch.distributed as dist

@@ -83,7 +83,7 @@ class TorchCudaBackend:
 class SweepEngine:
     """One batch of ``U`` equal-length (clean, noisy) pairs resident on one device."""
 
-    def __init__(self, clean, noisy, sr=SR, lib=None, backend=None, chunk_items=1184, prepare_scoring=True):
+    def __init__(self, clean, noisy, sr=SR, lib=None, backend=None, chunk_items=4736, prepare_scoring=True):
         if sr != SR:
             raise ValueError("the sweep runs at 16 kHz (the reference resamples every pair to 16 kHz first)")
         self.lib = lib if lib is not None else (_runtime["lib"] or _lib.load())

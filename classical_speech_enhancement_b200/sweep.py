@@ -53,7 +53,7 @@ def select_all(scores, points, pesq=None):
     return out
 
 
-def sweep_dataset(clean, noisy, grids=DEFAULT_GRIDS, sr=16000, select=True, chunk_items=1184, engine_kwargs=None):
+def sweep_dataset(clean, noisy, grids=DEFAULT_GRIDS, sr=16000, select=True, chunk_items=4736, engine_kwargs=None):
     """clean, noisy: host arrays [U, L] (equal-length, 16 kHz, pair-aligned).
 
     Returns ``{"scores", "points", "nominal", "unique", "selection", "engine"}``."""
