@@ -59,20 +59,23 @@ CSE_HD real r_min(real a, real b) { return fminf(a, b); }
 CSE_HD real r_floor(real x) { return floorf(x); }
 CSE_HD real r_fma(real a, real b, real c) { return fmaf(a, b, c); }
 #endif
-// Fast forms for the fp32 gain rules: one MUFU op each (rcp / lg2 / ex2 / rsq), relative error
-// <= ~2e-6 over the ranges the gain rules use - far inside the 1e-4 waveform budget.  The FP64
-// build and the CPU emulation use the exact forms.
+// Fast forms for the fp32 gain rules: ONE MUFU instruction each (rcp / lg2 / ex2 / rsq .approx.ftz,
+// relative error <= ~2e-7 .. 1e-6 over the ranges the gain rules use - far inside the 1e-4
+// waveform budget; no argument here is ever denormal).  The FP64 build and the CPU emulation use
+// the exact forms.
 #if defined(CSE_FP64) || defined(CSE_EMU)
 CSE_HD real r_rcp(real x) { return R(1) / x; }
-CSE_HD real r_fexp(real x) { return r_exp(x); }
-CSE_HD real r_flog(real x) { return r_log(x); }
+CSE_HD real r_fexp2(real x) { return (real)exp2((double)x); }
+CSE_HD real r_flog2(real x) { return (real)log2((double)x); }
 CSE_HD real r_fsqrt(real x) { return r_sqrt(x); }
 #else
-CSE_D real r_rcp(real x) { return __fdividef(1.0f, x); }
-CSE_D real r_fexp(real x) { return __expf(x); }
-CSE_D real r_flog(real x) { return __logf(x); }
-CSE_D real r_fsqrt(real x) { return x * rsqrtf(x); }
+CSE_D real r_rcp(real x) { real y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+CSE_D real r_fexp2(real x) { real y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+CSE_D real r_flog2(real x) { real y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+CSE_D real r_fsqrt(real x) { real y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return x * y; }
 #endif
+#define CSE_LOG2E R(1.44269504088896340736)
+#define CSE_LN2 R(0.69314718055994530942)
 // numpy's maximum/minimum/clip propagate NaN, fmax/fmin drop it.  The reference relies on
 // that only through np.nan_to_num, which the gain kernels restate explicitly.
 CSE_HD real r_clip(real x, real lo, real hi) { return r_min(r_max(x, lo), hi); }

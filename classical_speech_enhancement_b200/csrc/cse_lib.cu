@@ -129,6 +129,7 @@ static int enhance_items(const void* tables, int algorithm, const void* Y, const
     a.T = (const CseTables*)tables; a.Y = (const real2*)Y; a.N = (const real*)N; a.params = params;
     a.out = (real*)out; a.noise_tv = noise_tv; a.L = length; a.hop = hop;
     a.n_frames = cse_num_frames(length, hop); a.n_params = n_params; a.item0 = item0; a.eps = alg_eps(algorithm);
+    a.hop_shift = (hop & (hop - 1)) == 0 ? cse_ilog2(hop) : -1;
     switch (algorithm) {
         case CSE_ALG_SS: return dispatch_enhance<0>(a, n_fft, n_items, stream);
         case CSE_ALG_WIENER: return dispatch_enhance<1>(a, n_fft, n_items, stream);

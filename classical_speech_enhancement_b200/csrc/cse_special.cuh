@@ -46,21 +46,37 @@ CSE_HD real cse_expint_e1(real v) {
     return clenshaw(c, t) * r_exp(-v) / v;
 }
 
-// Device-side fast variants used by the gain kernels (fp32: MUFU-based rcp / log / exp).
+// Device-side fast variants used by the gain kernels.  fp32: power-basis Horner (one FFMA per
+// term, coefficients become FFMA immediates) + single-MUFU rcp / lg2 / ex2; fp64: the exact forms.
+template <int N> CSE_HD real horner(const real (&a)[N], real t) {
+    real r = a[N - 1];
+#pragma unroll
+    for (int k = N - 2; k >= 0; --k) r = r_fma(r, t, a[k]);
+    return r;
+}
+#ifdef CSE_FP64
+#define CSE_POLY_EVAL(name, t) clenshaw(c_##name, t)
+#define CSE_POLY_DECL(name) const real c_##name[CSE_COEF_N(name)] = CSE_COEF(name)
+#else
+#define CSE_POLY_EVAL(name, t) horner(c_##name, t)
+#define CSE_POLY_DECL(name) const real c_##name[CSE_##name##_F32_N] = CSE_##name##_F32_POLY
+#endif
+
 CSE_D real cse_mmse_bessel_term_fast(real v) {
     if (v <= R(16)) {
-        const real c[CSE_COEF_N(M_LO)] = CSE_COEF(M_LO);
-        return clenshaw(c, v * R(0.125) - R(1));
+        CSE_POLY_DECL(M_LO);
+        return CSE_POLY_EVAL(M_LO, v * R(0.125) - R(1));
     }
-    const real c[CSE_COEF_N(M_HI)] = CSE_COEF(M_HI);
-    return clenshaw(c, R(40) * r_rcp(v) - R(1.5)) * r_fsqrt(v);
+    CSE_POLY_DECL(M_HI);
+    return CSE_POLY_EVAL(M_HI, R(40) * r_rcp(v) - R(1.5)) * r_fsqrt(v);
 }
-CSE_D real cse_expint_e1_fast(real v) {
+// E1(v) * 0.5 * log2(e): the Log-MMSE gain is evaluated in the log2 domain
+CSE_D real cse_half_e1_log2_fast(real v) {
     if (v <= R(1)) {
-        const real c[CSE_COEF_N(E_LO)] = CSE_COEF(E_LO);
-        return clenshaw(c, v + v - R(1)) - r_flog(v);
+        CSE_POLY_DECL(E_LO);
+        return R(0.5) * (CSE_LOG2E * CSE_POLY_EVAL(E_LO, v + v - R(1)) - r_flog2(v));    // ln v = log2 v * ln 2
     }
-    const real c[CSE_COEF_N(E_HI)] = CSE_COEF(E_HI);
+    CSE_POLY_DECL(E_HI);
     const real rv = r_rcp(v);
-    return clenshaw(c, (rv + rv - R(1.0125)) * R(1.0 / 0.9875)) * r_fexp(-v) * rv;
+    return (R(0.5) * CSE_LOG2E) * CSE_POLY_EVAL(E_HI, (rv + rv - R(1.0125)) * R(1.0 / 0.9875)) * r_fexp2(-v * CSE_LOG2E) * rv;
 }

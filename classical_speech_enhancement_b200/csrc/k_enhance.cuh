@@ -62,12 +62,12 @@ CSE_D real2 gain_apply(real2 Yv, real Nraw, bool first, GainState& st, const rea
             const real A = R(0.88622692545275801365) * r_fsqrt(v) * r_rcp(gam + eps);
             G = r_clip(A * cse_mmse_bessel_term_fast(v), pv[2], pv[3]);
         } else {
-            const real gf = pv[2], q = pv[4], vmax = pv[5], lngf = pv[6];
+            const real gf = pv[2], q = pv[4], vmax = pv[5], lg2gf = pv[6];
             const real v = r_clip(xr * gam, R(1e-12), vmax);
-            const real lg = r_flog(xr) + R(0.5) * cse_expint_e1_fast(v);       // ln(G_lsa)
-            const real ql = r_fma(q, r_fexp(v) * r, eps);                       // q * Lambda + eps
+            const real lg2 = r_flog2(xr) + cse_half_e1_log2_fast(v);            // log2(G_lsa)
+            const real ql = r_fma(q, r_fexp2(v * CSE_LOG2E) * r, eps);          // q * Lambda + eps
             const real p = r_clip(ql * r_rcp(ql + (R(1) - q)), R(0), R(1));     // 1 / (1 + (1-q)/ql)
-            G = r_clip(r_fexp(r_fma(p, lg - lngf, lngf)), gf, R(1));            // G_lsa^p gf^(1-p)
+            G = r_clip(r_fexp2(r_fma(p, lg2 - lg2gf, lg2gf)), gf, R(1));        // G_lsa^p gf^(1-p)
         }
     }
     st.g_prev = G;
@@ -82,6 +82,7 @@ struct EnhanceArgs {
     const cse_params* params;
     real* out;           // [(item - item0)][L]
     int noise_tv, L, hop, n_frames, n_params, item0;
+    int hop_shift;       // log2(hop) when hop is a power of two, else -1
     real eps;
 };
 
@@ -133,7 +134,7 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (LOG2N >= 10 ? 3 : 4)) 
         wsteady[r] = s;
     }
     __syncthreads();
-    if (ALG == 3 && tid == 0) pv_s[6] = r_log(pv_s[2]);
+    if (ALG == 3 && tid == 0) pv_s[6] = r_log(pv_s[2]) * CSE_LOG2E;     // log2(gain_floor)
     __syncthreads();
     real pv[8];
 #pragma unroll
@@ -246,8 +247,8 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (LOG2N >= 10 ? 3 : 4)) 
 #pragma unroll
                     for (int e = 0; e < 2; ++e) {
                         const int pe = p + e;
-                        const int tmax = pe / hop, r = pe - tmax * hop;
-                        const int kmax = (NFFT - 1 - r) / hop;          // frames tmax-k, k <= kmax, cover pe
+                        const int tmax = a.hop_shift >= 0 ? (pe >> a.hop_shift) : pe / hop, r = pe - tmax * hop;
+                        const int kmax = a.hop_shift >= 0 ? ((NFFT - 1 - r) >> a.hop_shift) : (NFFT - 1 - r) / hop;   // frames tmax-k, k <= kmax, cover pe
                         if (tmax - kmax >= 0 && tmax < nf) ws[e] = wsteady[r];
                         else {
                             real s = R(0);
