@@ -33,16 +33,16 @@ CSE_D real2 tw_load(const real2* __restrict__ tw, int idx) {
 template <int m> CSE_D real2 rot8(real2 d) {
     const real h = R(0.70710678118654752440);
     if (m == 0) return d;
-    if (m == 1) return mk2((d.x + d.y) * h, (d.y - d.x) * h);     // * (1 - i)/sqrt2
+    if (m == 1) return cscale(cadd(d, mk2(d.y, -d.x)), h);          // * (1 - i)/sqrt2
     if (m == 2) return mk2(d.y, -d.x);                             // * (-i)
-    return mk2((d.y - d.x) * h, -(d.x + d.y) * h);                 // * (-1 - i)/sqrt2
+    return cscale(cadd(mk2(-d.x, -d.y), mk2(d.y, -d.x)), h);       // * (-1 - i)/sqrt2
 }
 template <int m> CSE_D real2 rot8c(real2 d) {   // conj(W_8^m)
     const real h = R(0.70710678118654752440);
     if (m == 0) return d;
-    if (m == 1) return mk2((d.x - d.y) * h, (d.x + d.y) * h);     // * (1 + i)/sqrt2
+    if (m == 1) return cscale(cadd(d, mk2(-d.y, d.x)), h);          // * (1 + i)/sqrt2
     if (m == 2) return mk2(-d.y, d.x);                             // * (+i)
-    return mk2(-(d.x + d.y) * h, (d.x - d.y) * h);                 // * (-1 + i)/sqrt2
+    return cscale(cadd(mk2(-d.x, -d.y), mk2(-d.y, d.x)), h);       // * (-1 + i)/sqrt2
 }
 
 template <bool CONJ> CSE_D real2 twmul(real2 a, real2 w) { return CONJ ? cmulc(a, w) : cmul(a, w); }

@@ -80,3 +80,35 @@ CSE_D real cse_half_e1_log2_fast(real v) {
     const real rv = r_rcp(v);
     return (R(0.5) * CSE_LOG2E) * CSE_POLY_EVAL(E_HI, (rv + rv - R(1.0125)) * R(1.0 / 0.9875)) * r_fexp2(-v * CSE_LOG2E) * rv;
 }
+
+// ---- two-lane forms (both range branches evaluated for both lanes, selected per lane) ----
+template <int N> CSE_D real2 horner2(const real (&a)[N], real2 t) {
+    real2 r = p_set(a[N - 1]);
+#pragma unroll
+    for (int k = N - 2; k >= 0; --k) r = p_fma(r, t, p_set(a[k]));
+    return r;
+}
+#ifdef CSE_FP64
+template <int N> CSE_D real2 poly2(const real (&c)[N], real2 t) { return mk2(clenshaw(c, t.x), clenshaw(c, t.y)); }
+#else
+template <int N> CSE_D real2 poly2(const real (&a)[N], real2 t) { return horner2(a, t); }
+#endif
+CSE_D real2 cse_mmse_bessel_term2(real2 v) {
+    CSE_POLY_DECL(M_LO);
+    CSE_POLY_DECL(M_HI);
+    const real2 lo = poly2(c_M_LO, p_fma(v, p_set(R(0.125)), p_set(R(-1))));
+    const real2 vv = p_max(v, p_set(R(16)));                        // keep the high branch's argument in range
+    const real2 hi = p_mul(poly2(c_M_HI, p_fma(p_rcp(vv), p_set(R(40)), p_set(R(-1.5)))), p_sqrt(vv));
+    return mk2(v.x <= R(16) ? lo.x : hi.x, v.y <= R(16) ? lo.y : hi.y);
+}
+CSE_D real2 cse_half_e1_log2_2(real2 v) {
+    CSE_POLY_DECL(E_LO);
+    CSE_POLY_DECL(E_HI);
+    const real2 vl = p_min(v, p_set(R(1)));                         // each branch evaluated inside its own range
+    const real2 lo = p_mul(p_set(R(0.5)), p_sub(p_mul(p_set(CSE_LOG2E), poly2(c_E_LO, p_fma(vl, p_set(R(2)), p_set(R(-1))))), p_log2(vl)));
+    const real2 vh = p_max(v, p_set(R(1)));
+    const real2 rv = p_rcp(vh);
+    const real2 t = p_mul(p_fma(rv, p_set(R(2)), p_set(R(-1.0125))), p_set(R(1.0 / 0.9875)));
+    const real2 hi = p_mul(p_mul(p_set(R(0.5) * CSE_LOG2E), poly2(c_E_HI, t)), p_mul(p_exp2(p_mul(vh, p_set(-CSE_LOG2E))), rv));
+    return mk2(v.x <= R(1) ? lo.x : hi.x, v.y <= R(1) ? lo.y : hi.y);
+}

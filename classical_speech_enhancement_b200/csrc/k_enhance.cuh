@@ -75,6 +75,67 @@ CSE_D real2 gain_apply(real2 Yv, real Nraw, bool first, GainState& st, const rea
     return mk2(Yv.x * G, Yv.y * G);
 }
 
+// Two bins at once (the thread's pair (s, M-s)): lane .x = bin a, lane .y = bin b.  Same
+// arithmetic as gain_apply, with every FP add / mul / fma issued as one packed instruction for
+// both bins.  State is packed the same way.
+struct GainState2 { real2 g_prev, gam_prev, nsm; };
+
+template <int ALG>
+CSE_D void gain_pair(real2 Ya, real2 Yb, real2 Nraw, bool first, GainState2& st, const real* __restrict__ pv,
+                     real eps, bool smooth, real2& Sa, real2& Sb) {
+    const real2 re = mk2(Ya.x, Yb.x), im = mk2(Ya.y, Yb.y);
+    const real2 Pw = p_fma(re, re, p_mul(im, im));
+    real2 Nt = p_max(Nraw, p_set(eps));
+    if (ALG == 0) {
+        const real2 Pc = p_max(p_fma(p_set(-pv[0]), Nt, Pw), p_mul(p_set(pv[1]), Nt));
+        real g[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const real pw = e ? Pw.y : Pw.x, pc = e ? Pc.y : Pc.x;
+            g[e] = pw > R(1e-30) ? r_fsqrt(pc * r_rcp(pw)) : (pw > R(0) ? r_sqrt(pc) / r_sqrt(pw) : R(-1));
+        }
+        Sa = g[0] >= R(0) ? mk2(Ya.x * g[0], Ya.y * g[0]) : mk2(r_sqrt(Pc.x), R(0));
+        Sb = g[1] >= R(0) ? mk2(Yb.x * g[1], Yb.y * g[1]) : mk2(r_sqrt(Pc.y), R(0));
+        return;
+    }
+    if (ALG >= 2 && smooth) {
+        const real mu = (ALG == 2) ? pv[4] : pv[3];
+        if (!first) Nt = p_fma(p_set(mu), st.nsm, p_mul(p_set(R(1) - mu), Nt));
+        st.nsm = Nt;
+        Nt = p_max(Nt, p_set(eps));
+    }
+    const real2 gam = p_max(p_mul(Pw, p_rcp(Nt)), p_set(eps));
+    const real2 gm1 = p_add(gam, p_set(R(-1)));
+    const real2 direct = p_max(gm1, p_set(R(0)));
+    const real alpha = pv[0];
+    const real2 rec = p_fma(p_set(alpha), p_mul(p_mul(st.g_prev, st.g_prev), st.gam_prev), p_mul(p_set(R(1) - alpha), direct));
+    real2 G;
+    if (ALG == 1) {
+        const real2 xi = p_max(first ? direct : rec, p_set(R(1e-10)));
+        G = p_clip(p_mul(xi, p_rcp(p_add(xi, p_set(R(1))))), pv[1], R(1));
+    } else {
+        const real2 xi = p_max(first ? gm1 : rec, p_set(pv[1]));
+        const real2 r = p_rcp(p_add(xi, p_set(R(1))));
+        const real2 xr = p_mul(xi, r);
+        if (ALG == 2) {
+            const real2 v = p_clip(p_mul(xr, gam), eps, R(80));
+            const real2 A = p_mul(p_mul(p_set(R(0.88622692545275801365)), p_sqrt(v)), p_rcp(p_add(gam, p_set(eps))));
+            G = p_clip(p_mul(A, cse_mmse_bessel_term2(v)), pv[2], pv[3]);
+        } else {
+            const real gf = pv[2], q = pv[4], vmax = pv[5], lg2gf = pv[6];
+            const real2 v = p_clip(p_mul(xr, gam), R(1e-12), vmax);
+            const real2 lg2 = p_add(p_log2(xr), cse_half_e1_log2_2(v));
+            const real2 ql = p_fma(p_set(q), p_mul(p_exp2(p_mul(v, p_set(CSE_LOG2E))), r), p_set(eps));
+            const real2 p = p_clip(p_mul(ql, p_rcp(p_add(ql, p_set(R(1) - q)))), R(0), R(1));
+            G = p_clip(p_exp2(p_fma(p, p_add(lg2, p_set(-lg2gf)), p_set(lg2gf))), gf, R(1));
+        }
+    }
+    st.g_prev = G;
+    st.gam_prev = gam;
+    Sa = mk2(Ya.x * G.x, Ya.y * G.x);
+    Sb = mk2(Yb.x * G.y, Yb.y * G.y);
+}
+
 struct EnhanceArgs {
     const CseTables* T;
     const real2* Y;      // [U][nf][nbp]
@@ -148,7 +209,7 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (LOG2N >= 10 ? 3 : 4)) 
 
     const bool is_pair = tid < NTB, is_mid = tid == NTB;       // lane 0 of the extra warp: bin M/2
     const int n_slots = is_pair ? PPT : (is_mid ? 1 : 0);
-    GainState st[PPT][2];
+    GainState2 st[PPT];
     real nstat[PPT][2];
     real2 twc[PPT];                                           // W_N^s of each pair slot
     real2 yv[PPT][2][F];
@@ -159,7 +220,7 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (LOG2N >= 10 ? 3 : 4)) 
 #pragma unroll
     for (int i = 0; i < PPT; ++i) {
 #pragma unroll
-        for (int e = 0; e < 2; ++e) { st[i][e].g_prev = R(1); st[i][e].gam_prev = R(1); st[i][e].nsm = R(0); }
+        st[i].g_prev = mk2(R(1), R(1)); st[i].gam_prev = mk2(R(1), R(1)); st[i].nsm = mk2(R(0), R(0));
         nstat[i][0] = (!a.noise_tv && i < n_slots) ? Nu[bin_a(i)] : R(1);
         nstat[i][1] = (!a.noise_tv && is_pair) ? Nu[bin_b(i)] : R(1);
         twc[i] = tw_load(a.T->tw, (is_pair ? tid + i * NTB : 0) * (CSE_TW_N / NFFT));
@@ -203,9 +264,9 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (LOG2N >= 10 ? 3 : 4)) 
                             else xf[SIDX(M / 2)] = mk2(R(0), R(0));
                             continue;
                         }
-                        const real2 xa = gain_apply<ALG>(yv[i][0][f], nv[i][0][f], t == 0, st[i][0], pv, a.eps, smooth);
+                        real2 xa, xb;
+                        gain_pair<ALG>(yv[i][0][f], yv[i][1][f], mk2(nv[i][0][f], nv[i][1][f]), t == 0, st[i], pv, a.eps, smooth, xa, xb);
                         if (!is_pair) { xf[SIDX(M / 2)] = mk2(R(2) * xa.x, R(-2) * xa.y); continue; }   // 2 conj X[M/2]
-                        const real2 xb = gain_apply<ALG>(yv[i][1][f], nv[i][1][f], t == 0, st[i][1], pv, a.eps, smooth);
                         if (s == 0) { xf[0] = mk2(xa.x + xb.x, xa.x - xb.x); continue; }                // DC, Nyquist (real)
                         const real2 E = mk2(xa.x + xb.x, xa.y - xb.y);
                         const real2 D = mk2(xa.x - xb.x, xa.y + xb.y);

@@ -312,6 +312,58 @@ CSE_D void resample_pass(const real* __restrict__ sig, int L, int lag, bool fina
     __syncthreads();
 }
 
+// Candidate-path resampler: one pass produces y10[5a + p] for 512 groups a.  Each thread owns TWO
+// groups (al, al + 256) whose input samples sit side by side in a float2 tile, so one LDS.64 feeds
+// both and every tap is ONE packed FFMA2 (tap broadcast from the constant bank through a uniform
+// register): 581 FFMA2 + 123 LDS.64 per two groups instead of 2 x (581 FFMA + 123 LDS).
+#define CSE_RS_A2 512
+CSE_D void resample_pass2(const real* __restrict__ sig, int L, int lag, bool finalize, real2* xs2, int a0,
+                          real* __restrict__ y10, int n10, int tid, int nth, const unsigned char* __restrict__ need) {
+    constexpr int H = CSE_RS_A2 / 2, AP2 = H + 17;
+    const int j0 = 8 * a0 - 64;
+    // tile load: all global loads of the thread are issued before the first shared-memory store
+    constexpr int TOT = 8 * (CSE_RS_A2 + 17), PERT = (TOT + 255) / 256;
+    {
+        real v[PERT];
+#pragma unroll
+        for (int k = 0; k < PERT; ++k) { const int jj = tid + k * nth; v[k] = jj < TOT ? xhat(sig, j0 + jj, lag, L, finalize) : R(0); }
+#pragma unroll
+        for (int k = 0; k < PERT; ++k) {
+            const int jj = tid + k * nth;
+            if (jj < TOT) {
+                const int c = jj & 7, ap = jj >> 3;
+                if (ap < AP2) xs2[c * AP2 + ap].x = v[k];
+                if (ap >= H) xs2[c * AP2 + ap - H].y = v[k];
+            }
+        }
+    }
+    __syncthreads();
+    for (int al = tid; al < H; al += nth) {
+        const int alo = a0 + al, ahi = alo + H;
+        const bool want_lo = 5 * alo < n10 && need[alo], want_hi = 5 * ahi < n10 && need[ahi];
+        if (want_lo || want_hi) {
+            real2 acc[5];
+#pragma unroll
+            for (int p = 0; p < 5; ++p) acc[p] = mk2(R(0), R(0));
+#pragma unroll
+            for (int jj = 6; jj <= 128; ++jj) {                 // rows 0-5 and 129-135 hold no tap
+                const real2 x = xs2[(jj & 7) * AP2 + al + (jj >> 3)];
+#pragma unroll
+                for (int p = 0; p < 5; ++p) {
+                    const int idx = 8 * p + 610 - 5 * jj;        // compile-time after unrolling
+                    if (idx >= 0 && idx <= 580) acc[p] = cfma2(x, mk2(c_rs[jj * 8 + p], c_rs[jj * 8 + p]), acc[p]);
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < 5; ++p) {
+                if (want_lo && 5 * alo + p < n10) y10[5 * alo + p] = acc[p].x;
+                if (want_hi && 5 * ahi + p < n10) y10[5 * ahi + p] = acc[p].y;
+            }
+        }
+    }
+    __syncthreads();
+}
+
 // clean-side resampling + VAD (pystoi remove_silent_frames, mask from the clean signal only)
 // grid U, block 256; y10 (real) goes to the workspace for clean_stoi.
 __global__ void __launch_bounds__(256) clean_vad_kernel(ScoreArgs a, double* __restrict__ y10d, double* __restrict__ energies) {
@@ -399,8 +451,12 @@ __global__ void __launch_bounds__(256) stoi_kernel(ScoreArgs a, const double* __
     real* pw = reinterpret_cast<real*>(fbuf + T * BST);                       // T * NK
     real* ytob = pw + T * NK;                                                 // 15 * Kf
     real* xtob = ytob + CSE_NBANDS * (g.nfrm + 1);                            // 15 * Kf (MODE 0)
-    real* xs = reinterpret_cast<real*>(fbuf);
+    real* w_s = xtob + CSE_NBANDS * (g.nfrm + 1);                             // 256: np.hanning(258)[1:-1]
+    int* kept_s = reinterpret_cast<int*>(w_s + 256);                          // nfr + 2 kept-frame indices
 
+    for (int i = tid; i < 256; i += NT) w_s[i] = a.T->stoi_win[i];
+    for (int i = tid; i < K; i += NT) kept_s[i] = kept[i];
+    __syncthreads();
     const real* __restrict__ sig = a.wav + (size_t)li * g.L;
     real* y10 = a.y10 + (size_t)li * g.n10;
     int lag = 0, flags = CSE_FLAG_VALID;
@@ -413,11 +469,20 @@ __global__ void __launch_bounds__(256) stoi_kernel(ScoreArgs a, const double* __
         const real* __restrict__ cl = a.clean + (size_t)u * g.L;
         real pn = R(0);
         int bad = 0;
-        for (int i = tid; i < g.L; i += NT) {
-            const real raw = xraw(sig, i, lag, g.L);
-            if (!r_finite(raw)) bad = 1;
-            const real d = cl[i] - (fin ? r_clip(raw, R(-1), R(1)) : raw);
-            pn = r_fma(d, d, pn);
+        for (int i0 = 0; i0 < g.L; i0 += 4 * NT) {
+            real raw[4], cv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + tid + k * NT;
+                raw[k] = i < g.L ? xraw(sig, i, lag, g.L) : R(0);
+                cv[k] = i < g.L ? cl[i] : R(0);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (!r_finite(raw[k])) bad = 1;
+                const real d = cv[k] - (fin ? r_clip(raw[k], R(-1), R(1)) : raw[k]);
+                pn = r_fma(d, d, pn);
+            }
         }
         const double nbad = block_sum<double>((double)bad, scratch);
         if (nbad > 0.0) {
@@ -428,8 +493,8 @@ __global__ void __launch_bounds__(256) stoi_kernel(ScoreArgs a, const double* __
         for (int i = tid; i < CSE_NBANDS * Kf; i += NT) xtob[i] = xtob_c[i];
         __syncthreads();
         const int na = (g.n10 + 4) / 5;
-        for (int a0 = 0; a0 < na; a0 += CSE_RS_A)
-            resample_pass<real, real, real, true>(sig, g.L, lag, fin, (const real*)nullptr, xs, a0, y10, g.n10, tid, NT, need);
+        for (int a0 = 0; a0 < na; a0 += CSE_RS_A2)
+            resample_pass2(sig, g.L, lag, fin, reinterpret_cast<real2*>(fbuf), a0, y10, g.n10, tid, NT, need);
         __threadfence_block();
         __syncthreads();
         if (tid == 0) {
@@ -444,7 +509,6 @@ __global__ void __launch_bounds__(256) stoi_kernel(ScoreArgs a, const double* __
         if (MODE == 0 && tid == 0) { a.scores[item].stoi = R(1e-5); a.scores[item].flags = flags | CSE_FLAG_STOI_SHORT; }
         return;
     }
-    const real* __restrict__ w = a.T->stoi_win;
     const int* __restrict__ edges = a.T->stoi_edges;
     const double* ydu = MODE == 1 ? y10d + (size_t)u * g.n10 : nullptr;
     auto ysamp = [&](int i) -> real { return MODE == 1 ? (real)ydu[i] : y10[i]; };
@@ -453,23 +517,33 @@ __global__ void __launch_bounds__(256) stoi_kernel(ScoreArgs a, const double* __
         // frames of the silence-removed signal: sample n of frame m is
         //   w[n] * (F_m[n] + F_{m-1}[n+128])  (n < 128),  w[n] * (F_{m+1}[n-128] + F_m[n])  (n >= 128),
         // F_j[n] = w[n] * y10[128 kept[j] + n]
-        for (int idx = tid; idx < T * 256; idx += NT) {
-            const int f = idx >> 8, mm = idx & 255, m = m0 + f;
-            real2 v = mk2(R(0), R(0));
-            if (mm < 128 && m < Kf) {
-                const int kc = 128 * kept[m];
-                real s[2];
+        // frame m = w .* (B_m ++ B_{m+1}), B_j[n] = w[n] y10[128 kept[j] + n] + w[128+n] y10[128 kept[j-1] + 128 + n]
+        // (the overlap-added blocks of the silence-removed signal).  4 packed samples per thread, all
+        // y10 loads issued first.
+        {
+            constexpr int PER = T * 128 / NT;
+            real ya[PER][2], yb[PER][2];
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const int n = 2 * mm + e;
-                    real acc = w[n] * ysamp(kc + n);
-                    if (n < 128) { if (m > 0) acc += w[n + 128] * ysamp(128 * kept[m - 1] + n + 128); }
-                    else acc += w[n - 128] * ysamp(128 * kept[m + 1] + n - 128);
-                    s[e] = w[n] * acc;
-                }
-                v = mk2(s[0], s[1]);
+            for (int k = 0; k < PER; ++k) {
+                const int idx = tid + k * NT, f = idx >> 7, mm = idx & 127, m = m0 + f;
+                const int j = mm < 64 ? m : m + 1, nn = (2 * mm) & 127;
+                const bool on = m < Kf;
+                const int k1 = on ? 128 * kept_s[j] + nn : 0;
+                const int k0 = (on && j > 0) ? 128 * kept_s[j - 1] + 128 + nn : -1;
+                ya[k][0] = on ? ysamp(k1) : R(0);
+                ya[k][1] = on ? ysamp(k1 + 1) : R(0);
+                yb[k][0] = k0 >= 0 ? ysamp(k0) : R(0);
+                yb[k][1] = k0 >= 0 ? ysamp(k0 + 1) : R(0);
             }
-            fbuf[f * BST + SIDX(mm)] = v;
+#pragma unroll
+            for (int k = 0; k < PER; ++k) {
+                const int idx = tid + k * NT, f = idx >> 7, mm = idx & 127;
+                const int nn = (2 * mm) & 127, n = 2 * mm;
+                const real b0 = r_fma(w_s[nn], ya[k][0], w_s[nn + 128] * yb[k][0]);
+                const real b1 = r_fma(w_s[nn + 1], ya[k][1], w_s[nn + 129] * yb[k][1]);
+                fbuf[f * BST + SIDX(mm)] = mk2(w_s[n] * b0, w_s[n + 1] * b1);
+                fbuf[f * BST + SIDX(mm + 128)] = mk2(R(0), R(0));
+            }
         }
         __syncthreads();
         fft_dif<8, false>(fbuf, T, BST, a.T->tw, tid, NT);

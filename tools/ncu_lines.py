@@ -44,5 +44,5 @@ for r in rows:
 tot = sum(v[0] for v in agg.values()) or 1
 tots = sum(v[1] for v in agg.values()) or 1
 print(f"total warp-inst {tot}, samples {tots}")
-for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:top]:
+for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1 if len(sys.argv) > 4 else 0])[:top]:
     print(f"{v[0] / tot:6.1%} inst {v[1] / tots:6.1%} smp  bar {v[2]:6d} excess_smem {v[3]:9d}  {k[1]}:{k[2]}  {k[3]}")
