@@ -62,11 +62,12 @@ CSE_D void dif_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
     for (int idx = tid; idx < total; idx += nth) {
         const int b = idx / per, r = idx - b * per;
         const int j = r & (q - 1), grp = r / q;
-        real2* p = s + b * bstride;
-        const int base = grp * (q * NB) + j;
+        // SIDX(base + m q) == SIDX(base) + SIDX(m q): base = grp*NB*q + j with j < q, q a power of two,
+        // so neither the >>4 nor the >>8 term of the padding ever carries across the addition.
+        real2* p = s + b * bstride + SIDX(grp * (q * NB) + j);
         real2 v[NB];
 #pragma unroll
-        for (int m = 0; m < NB; ++m) v[m] = p[SIDX(base + m * q)];
+        for (int m = 0; m < NB; ++m) v[m] = p[SIDX(m * q)];
         if (RL == 3) {
             const real2 w1 = tw_load(tw, j * twstep), w2 = tw_load(tw, j * twstep * 2), w3 = tw_load(tw, j * twstep * 4);
             real2 d;
@@ -93,7 +94,7 @@ CSE_D void dif_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
             real2 d = csub(v[0], v[1]); v[0] = cadd(v[0], v[1]); v[1] = twmul<CONJ>(d, w1);
         }
 #pragma unroll
-        for (int m = 0; m < NB; ++m) p[SIDX(base + m * q)] = v[m];
+        for (int m = 0; m < NB; ++m) p[SIDX(m * q)] = v[m];
     }
 }
 
@@ -109,11 +110,10 @@ CSE_D void dit_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
     for (int idx = tid; idx < total; idx += nth) {
         const int b = idx / per, r = idx - b * per;
         const int j = r & (q - 1), grp = r / q;
-        real2* p = s + b * bstride;
-        const int base = grp * (q * NB) + j;
+        real2* p = s + b * bstride + SIDX(grp * (q * NB) + j);      // affine storage offsets, see dif_pass
         real2 v[NB];
 #pragma unroll
-        for (int m = 0; m < NB; ++m) v[m] = p[SIDX(base + m * q)];
+        for (int m = 0; m < NB; ++m) v[m] = p[SIDX(m * q)];
         if (RL == 3) {
             // distances q (W_{2q}^j), 2q (W_{4q}^{j + (m&1)q}), 4q (W_{8q}^{j + (m&3)q}); conjugated
             const real2 w3 = tw_load(tw, j * twq), w2 = tw_load(tw, j * (twq >> 1)), w1 = tw_load(tw, j * (twq >> 2));
@@ -141,7 +141,7 @@ CSE_D void dit_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
             real2 t = twmul<CONJ>(v[1], w1); v[1] = csub(v[0], t); v[0] = cadd(v[0], t);
         }
 #pragma unroll
-        for (int m = 0; m < NB; ++m) p[SIDX(base + m * q)] = v[m];
+        for (int m = 0; m < NB; ++m) p[SIDX(m * q)] = v[m];
     }
 }
 

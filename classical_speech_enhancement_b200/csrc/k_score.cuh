@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(256) clean_vad_kernel(ScoreArgs a, double* __r
 // MODE 0: score a candidate.  MODE 1: clean-side pass (band envelopes + segment statistics into
 // the cache; y10 already in the workspace as double).
 template <int MODE>
-__global__ void __launch_bounds__(256) stoi_kernel(ScoreArgs a, const double* __restrict__ y10d) {
+__global__ void __launch_bounds__(256, 4) stoi_kernel(ScoreArgs a, const double* __restrict__ y10d) {
     constexpr int T = CSE_STOI_T, BST = CSE_FFT_STRIDE(256), NK = CSE_STOI_K1 - CSE_STOI_K0, NT = 256;
     CSE_DYN_SMEM(smem_raw);
     const ScoreGeom& g = a.g;
