@@ -321,37 +321,56 @@ def main():
     h2d = out["engine"].h2d_bytes
     d2h = sum(v.nbytes for v in out["scores"].values())
 
-    # ---------------- roofline of the dominant kernel family (events around every chunk launch)
-    fam = {}
+    # ---------------- roofline of the dominant kernel (events around every chunk launch, timed steps only)
+    names = {0: "ss", 1: "wiener", 2: "mmse", 3: "omlsa"}
+    fam, tags = {}, {}
     for (kind, alg, n_fft, hop, method), (items, ms) in timing.items():
         _, eb, sb = config_bytes(n_fft, hop, method, L)
+        # byte model per kernel: enhance = Y + noise PSD + waveform write; stoi = waveform read + scores
+        # (the "score" stage of SURVEY 8d); align re-reads the 2 s correlation window (an extra read the
+        # survey's count-once model does not include - listed for completeness).
+        per = eb if kind == "enhance" else (sb if kind == "stoi" else 4 * min(L, 32000))
+        by = items * per
         f = fam.setdefault(kind, [0.0, 0.0, 0])
-        f[0] += items * (eb if kind == "enhance" else sb)
-        f[1] += ms
-        f[2] += items
-    peaks = {}
+        f[0] += by; f[1] += ms; f[2] += items
+        kname = (f"enhance_kernel<{alg}, {n_fft.bit_length() - 1}>" if kind == "enhance" else f"{kind}_kernel<0>")
+        t = tags.setdefault(kname, [0.0, 0.0, 0, per])
+        t[0] += by; t[1] += ms; t[2] += items
+    peaks, traffic_tab = {}, {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    try:
+        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    dom = max(fam, key=lambda k: fam[k][1]) if fam else None
     roofline = None
-    if dom:
-        by, ms, items = fam[dom]
+    if tags:
+        dom = max(tags, key=lambda k: tags[k][1])
+        by, ms, items, _ = tags[dom]
+        launches_dom = max(1, -(-items // args.chunk))
         ach = by / (ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": {"enhance": "enhance_kernel<ALG,LOG2N,F> (gain + ISTFT)",
-                                               "score": "align_kernel + stoi_kernel"}[dom],
-                    "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                    "peak_source": peak_kind,
+        tr = traffic_tab.get(dom)
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": (tr["dram_bytes_per_item"] * items / launches_dom) if tr else None,
+                    "algorithmic_bytes_per_launch": by / launches_dom, "avg_launch_ms": ms / launches_dom,
+                    "launches": launches_dom, "peak_source": peak_kind,
                     "share_of_step": ms / (dev_ms if dev_ms > 0 else 1.0),
+                    "traffic_source": tr.get("source") if tr else None,
                     "families": {k: {"ms": v[1], "algorithmic_GBps": v[0] / (v[1] * 1e-3) / 1e9 if v[1] else None,
-                                     "items": v[2]} for k, v in fam.items()},
+                                     "items": v[2], "share_of_step": v[1] / (dev_ms if dev_ms > 0 else 1.0)}
+                                 for k, v in fam.items()},
+                    "kernels": {k: {"ms": v[1], "algorithmic_GBps": v[0] / (v[1] * 1e-3) / 1e9 if v[1] else None,
+                                    "us_per_item": 1e3 * v[1] / v[2]} for k, v in sorted(tags.items(), key=lambda kv: -kv[1][1])},
                     "whole_path": {"bytes_per_config": mean_bytes,
                                    "achieved": total_configs / step_s * mean_bytes / 1e9 / world,
                                    "frac": total_configs / step_s * mean_bytes / 1e9 / world / peak,
-                                   "note": "per GPU; nominal configs x grid-mean algorithmic bytes (SURVEY 8d)"}}
+                                   "note": "per GPU; nominal configs x grid-mean algorithmic bytes (SURVEY 8d)"},
+                    "note": "instruction-issue-bound kernels (see DESIGN.md section 6): DRAM traffic is far below the "
+                            "algorithmic bytes because Y / noise PSD are shared by all candidates of an utterance and hit in L2"}
 
     if rank == 0:
         cpu = None

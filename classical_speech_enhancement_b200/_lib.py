@@ -42,6 +42,8 @@ SIGNATURES = {
     "cse_sweep_workspace_bytes": (_sz, [_i, _i, _i]),
     "cse_enhance_items": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
     "cse_score_items": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "cse_align_items": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "cse_stoi_items": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "cse_debug_special": (_i, [_i, _vp, _vp, _i]),
     "cse_sweep": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
 }

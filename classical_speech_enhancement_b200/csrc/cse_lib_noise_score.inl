@@ -126,10 +126,12 @@ extern "C" size_t cse_score_workspace_bytes(int n_items, int length, int sr) {
     return up64((size_t)n_items * g.n10 * sizeof(real)) + up64((size_t)n_items * 2 * sizeof(int));
 }
 
-// scores items [item0, item0 + n_items); wav holds only those items
+// scores items [item0, item0 + n_items); wav holds only those items.  which: 1 = alignment kernel,
+// 2 = SNR/STOI kernel, 3 = both (the stoi kernel consumes the lag / flags the alignment kernel left
+// in the workspace).
 static int score_items(const void* tables, const void* wav, int item0, int n_items, int per_utt, int length,
                        const void* clean, const void* cache, int finalize, cse_score_t* scores, void* workspace,
-                       void* stream) {
+                       void* stream, int which = 3) {
     ScoreArgs a;
     memset(&a, 0, sizeof(a));
     a.T = (const CseTables*)tables; a.wav = (const real*)wav; a.clean = (const real*)clean;
@@ -138,12 +140,16 @@ static int score_items(const void* tables, const void* wav, int item0, int n_ite
     if (stoi_smem(a.g) > CSE_MAX_SMEM) return fail(CSE_EUNSUPPORTED, "utterance too long for the STOI kernel's shared memory (%d samples)", length);
     a.y10 = (real*)workspace;
     a.lagflags = (int*)((unsigned char*)workspace + up64((size_t)n_items * a.g.n10 * sizeof(real)));
-    auto ka = align_kernel<false>;
-    cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)align_smem());
-    CSE_LAUNCH(ka, n_items, 512, align_smem(), stream, a);
-    auto ks = stoi_kernel<0>;
-    cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stoi_smem(a.g));
-    CSE_LAUNCH(ks, n_items, 256, stoi_smem(a.g), stream, a, (const double*)nullptr);
+    if (which & 1) {
+        auto ka = align_kernel<false>;
+        cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)align_smem());
+        CSE_LAUNCH(ka, n_items, 512, align_smem(), stream, a);
+    }
+    if (which & 2) {
+        auto ks = stoi_kernel<0>;
+        cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stoi_smem(a.g));
+        CSE_LAUNCH(ks, n_items, 256, stoi_smem(a.g), stream, a, (const double*)nullptr);
+    }
     return check_launch("score");
 }
 
@@ -204,6 +210,27 @@ extern "C" int cse_score_items(const void* tables, const void* wav, int item0, i
     if (int rc = check_sr(sr)) return rc;
     if (workspace_bytes < cse_score_workspace_bytes(n_items, length, sr)) return fail(CSE_EWORKSPACE, "score workspace too small");
     return score_items(tables, wav, item0, n_items, per_utt, length, clean, cache, finalize, scores, workspace, stream);
+}
+
+// The two halves of cse_score_items as separate launches (same arguments), so that a caller can
+// bracket each kernel with its own events: cse_align_items first, then cse_stoi_items.
+extern "C" int cse_align_items(const void* tables, const void* wav, int item0, int n_items, int per_utt, int length,
+                               int sr, const void* clean, const void* cache, int finalize, cse_score_t* scores,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    CSE_REQUIRE(tables && wav && clean && cache && scores && workspace, "NULL argument");
+    CSE_REQUIRE(n_items > 0 && item0 >= 0 && per_utt > 0 && length > 0, "bad sizes");
+    if (int rc = check_sr(sr)) return rc;
+    if (workspace_bytes < cse_score_workspace_bytes(n_items, length, sr)) return fail(CSE_EWORKSPACE, "score workspace too small");
+    return score_items(tables, wav, item0, n_items, per_utt, length, clean, cache, finalize, scores, workspace, stream, 1);
+}
+extern "C" int cse_stoi_items(const void* tables, const void* wav, int item0, int n_items, int per_utt, int length,
+                              int sr, const void* clean, const void* cache, int finalize, cse_score_t* scores,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+    CSE_REQUIRE(tables && wav && clean && cache && scores && workspace, "NULL argument");
+    CSE_REQUIRE(n_items > 0 && item0 >= 0 && per_utt > 0 && length > 0, "bad sizes");
+    if (int rc = check_sr(sr)) return rc;
+    if (workspace_bytes < cse_score_workspace_bytes(n_items, length, sr)) return fail(CSE_EWORKSPACE, "score workspace too small");
+    return score_items(tables, wav, item0, n_items, per_utt, length, clean, cache, finalize, scores, workspace, stream, 2);
 }
 
 // ------------------------------------------------------------------ host-side probes for tests

@@ -258,11 +258,15 @@ class SweepEngine:
                 lib_.enhance_items(be.ptr(self.tables), alg, be.ptr(Y), be.ptr(N), int(tv), self.L, n_fft, hop,
                                    be.ptr(params), len(rows), i0, n, be.ptr(wav), be.stream())
                 t1 = self._tick()
-                lib_.score_items(be.ptr(self.tables), be.ptr(wav), i0, n, len(rows), self.L, SR, be.ptr(self.clean),
-                                 be.ptr(self.cache), 1, be.ptr(scores), be.ptr(ws), nbytes, be.stream())
+                sargs = (be.ptr(self.tables), be.ptr(wav), i0, n, len(rows), self.L, SR, be.ptr(self.clean),
+                         be.ptr(self.cache), 1, be.ptr(scores), be.ptr(ws), nbytes, be.stream())
+                lib_.align_items(*sargs)
                 t2 = self._tick()
+                lib_.stoi_items(*sargs)
+                t3 = self._tick()
                 self._record(("enhance", alg, n_fft, hop, key[2]), n, t0, t1)
-                self._record(("score", alg, n_fft, hop, key[2]), n, t1, t2)
+                self._record(("align", alg, n_fft, hop, key[2]), n, t1, t2)
+                self._record(("stoi", alg, n_fft, hop, key[2]), n, t2, t3)
                 self.launches += 3
             pending.append((g, scores, params))
         for g, scores, _ in pending:

@@ -144,6 +144,15 @@ int cse_score_items(const void* tables, const void* wav, int item0, int n_items,
                     int length, int sr, const void* clean, const void* cache, int finalize,
                     cse_score_t* scores, void* workspace, size_t workspace_bytes, void* stream);
 
+/* cse_score_items as its two kernels (alignment first, then SNR + STOI, which reads the lag and
+ * flags the alignment left in the workspace): same arguments. */
+int cse_align_items(const void* tables, const void* wav, int item0, int n_items, int per_utt,
+                    int length, int sr, const void* clean, const void* cache, int finalize,
+                    cse_score_t* scores, void* workspace, size_t workspace_bytes, void* stream);
+int cse_stoi_items(const void* tables, const void* wav, int item0, int n_items, int per_utt,
+                   int length, int sr, const void* clean, const void* cache, int finalize,
+                   cse_score_t* scores, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Host-side probe used by the tests: evaluates the special-function fits the gain kernels
  * inline (which = 0: exp(-v/2)[(1+v)I0(v/2)+vI1(v/2)] of Code/mmse.py:92-96; 1: E1(v) of
  * Code/advanced_mmse.py:103) at x[0..n) in the library's precision. */

@@ -33,7 +33,7 @@ names = {0: "ss", 1: "wiener", 2: "mmse", 3: "omlsa"}
 rows = []
 for (kind, alg, n_fft, hop, method), (items, ms) in eng.timing_summary().items():
     _, eb, sb = config_bytes(n_fft, hop, method, a.length)
-    by = items * (eb if kind == "enhance" else sb)
+    by = items * (eb if kind == "enhance" else (sb if kind == "stoi" else 4 * min(a.length, 32000)))
     rows.append((ms, kind, names[alg], n_fft, hop, method, items, 1e3 * ms / items, by / (ms * 1e-3) / 1e9))
 rows.sort(reverse=True)
 print(f"total step {total:.1f} ms for {a.utts} utterances ({a.utts * 9744 / total * 1e3:.0f} nominal configs/s)")

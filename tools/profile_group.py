@@ -36,6 +36,6 @@ for rep in range(a.reps):
     torch.cuda.synchronize()
     for (kind, alg, n_fft, hop, method), (items, ms) in sorted(eng.timing_summary().items()):
         _, eb, sb = config_bytes(n_fft, hop, method, a.length)
-        by = items * (eb if kind == "enhance" else sb)
+        by = items * (eb if kind == "enhance" else (sb if kind == "stoi" else 4 * min(a.length, 32000)))
         print(f"rep {rep} {kind:8s} items {items:6d} {ms:8.3f} ms {1e3 * ms / items:7.3f} us/item "
               f"{by / (ms * 1e-3) / 1e9:8.1f} algGB/s")
