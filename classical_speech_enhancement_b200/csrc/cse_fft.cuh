@@ -21,13 +21,7 @@
 #define SIDX(i) ((i) + ((i) >> 4) + ((i) >> 8))
 #define CSE_FFT_STRIDE(n) ((n) + ((n) >> 4) + ((n) >> 8) + 1)
 
-CSE_D real2 tw_load(const real2* __restrict__ tw, int idx) {
-#ifdef CSE_EMU
-    return tw[idx];
-#else
-    return __ldg(tw + idx);
-#endif
-}
+CSE_D real2 tw_load(const real2* __restrict__ tw, int idx) { return tw[idx]; }
 
 // W_8^m for m = 0..3 applied to d
 template <int m> CSE_D real2 rot8(real2 d) {
@@ -50,7 +44,7 @@ template <int m, bool CONJ> CSE_D real2 rotf(real2 d) { return CONJ ? rot8c<m>(d
 
 // One pass of RL fused DIF stages (CONJ: conjugated twiddles = inverse transform).  `h` = half size of the first fused stage,
 // q = h >> (RL-1) = smallest butterfly distance of the pass.
-template <int LOG2N, int RL, bool CONJ, int H>
+template <int LOG2N, int RL, bool CONJ, int H, int TWN>
 CSE_D void dif_pass(real2* s, int nbatch, int bstride, const real2* __restrict__ tw, int tid, int nth) {
     constexpr int N = 1 << LOG2N;
     constexpr int NB = 1 << RL;               // elements per butterfly
@@ -58,7 +52,7 @@ CSE_D void dif_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
     constexpr int q = h >> (RL - 1);
     constexpr int per = N / NB;
     const int total = nbatch * per;
-    constexpr int twstep = (CSE_TW_N / 2) / h;    // W_{2h}^p = W_T^{p * T/(2h)}
+    constexpr int twstep = (TWN / 2) / h;         // W_{2h}^p = W_T^{p * T/(2h)}, T = TWN = period of the table
     for (int idx = tid; idx < total; idx += nth) {
         const int b = idx / per, r = idx - b * per;
         const int j = r & (q - 1), grp = r / q;
@@ -99,14 +93,14 @@ CSE_D void dif_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
 }
 
 // One pass of RL fused DIT stages; q = half size of the FIRST (smallest) fused stage.
-template <int LOG2N, int RL, bool CONJ, int Q>
+template <int LOG2N, int RL, bool CONJ, int Q, int TWN>
 CSE_D void dit_pass(real2* s, int nbatch, int bstride, const real2* __restrict__ tw, int tid, int nth) {
     constexpr int N = 1 << LOG2N;
     constexpr int NB = 1 << RL;
     constexpr int q = Q;
     constexpr int per = N / NB;
     const int total = nbatch * per;
-    constexpr int twq = (CSE_TW_N / 2) / q;       // W_{2q}^p = W_T^{p * T/(2q)}
+    constexpr int twq = (TWN / 2) / q;            // W_{2q}^p = W_T^{p * T/(2q)}
     for (int idx = tid; idx < total; idx += nth) {
         const int b = idx / per, r = idx - b * per;
         const int j = r & (q - 1), grp = r / q;
@@ -148,29 +142,37 @@ CSE_D void dit_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
 // Decimation-in-frequency transform, natural-order in -> bit-reversed out.  INV=false: forward
 // (e^-j); INV=true: unnormalised inverse (e^+j).  Ends with a __syncthreads().  Stage sizes are
 // template constants so that all index arithmetic folds to shifts and masks.
-template <int LOG2N, bool INV>
+template <int LOG2N, bool INV, int TWN = CSE_TW_N>
 CSE_D void fft_dif(real2* s, int nbatch, int bstride, const real2* __restrict__ tw, int tid, int nth) {
     constexpr int REM = LOG2N % 3, NP = LOG2N / 3;
     constexpr int H0 = 1 << (LOG2N - 1), H1 = H0 >> REM;
-    if constexpr (REM == 1) { dif_pass<LOG2N, 1, INV, H0>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
-    if constexpr (REM == 2) { dif_pass<LOG2N, 2, INV, H0>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
-    if constexpr (NP >= 1) { dif_pass<LOG2N, 3, INV, H1>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
-    if constexpr (NP >= 2) { dif_pass<LOG2N, 3, INV, (H1 >> 3)>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
-    if constexpr (NP >= 3) { dif_pass<LOG2N, 3, INV, (H1 >> 6)>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
-    if constexpr (NP >= 4) { dif_pass<LOG2N, 3, INV, (H1 >> 9)>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (REM == 1) { dif_pass<LOG2N, 1, INV, H0, TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (REM == 2) { dif_pass<LOG2N, 2, INV, H0, TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 1) { dif_pass<LOG2N, 3, INV, H1, TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 2) { dif_pass<LOG2N, 3, INV, (H1 >> 3), TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 3) { dif_pass<LOG2N, 3, INV, (H1 >> 6), TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 4) { dif_pass<LOG2N, 3, INV, (H1 >> 9), TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
 }
 
 // Decimation-in-time transform, bit-reversed in -> natural-order out.  Ends with a __syncthreads().
-template <int LOG2N, bool INV>
+template <int LOG2N, bool INV, int TWN = CSE_TW_N>
 CSE_D void fft_dit(real2* s, int nbatch, int bstride, const real2* __restrict__ tw, int tid, int nth) {
     constexpr int REM = LOG2N % 3, NP = LOG2N / 3;
-    if constexpr (NP >= 1) { dit_pass<LOG2N, 3, INV, 1>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
-    if constexpr (NP >= 2) { dit_pass<LOG2N, 3, INV, 8>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
-    if constexpr (NP >= 3) { dit_pass<LOG2N, 3, INV, 64>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
-    if constexpr (NP >= 4) { dit_pass<LOG2N, 3, INV, 512>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 1) { dit_pass<LOG2N, 3, INV, 1, TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 2) { dit_pass<LOG2N, 3, INV, 8, TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 3) { dit_pass<LOG2N, 3, INV, 64, TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 4) { dit_pass<LOG2N, 3, INV, 512, TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
     constexpr int QR = 1 << (3 * NP);
-    if constexpr (REM == 2) { dit_pass<LOG2N, 2, INV, QR>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
-    if constexpr (REM == 1) { dit_pass<LOG2N, 1, INV, QR>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (REM == 2) { dit_pass<LOG2N, 2, INV, QR, TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (REM == 1) { dit_pass<LOG2N, 1, INV, QR, TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+}
+
+// Compact twiddle table W_N^k, k < N/2, copied from the global W_8192 table into shared memory: a
+// warp's twiddle reads in the wide-stride passes would otherwise touch up to 32 different
+// 128-byte lines of the global table per instruction (profiles/r01e: L1TEX 71 % busy).
+template <int N>
+CSE_D void load_twiddles(real2* dst, const real2* __restrict__ tw_global, int tid, int nth) {
+    for (int k = tid; k < N / 2; k += nth) dst[k] = tw_global[k * (CSE_TW_N / N)];
 }
 
 CSE_D int brev_n(int k, int log2n) { return (int)(__brev((unsigned)k) >> (32 - log2n)); }

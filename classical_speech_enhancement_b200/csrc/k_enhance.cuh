@@ -174,6 +174,8 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (LOG2N >= 10 ? 3 : 4)) 
     const int W = NFFT + (F - 1) * hop;
     real* wsteady = ring + W;                                          // hop: steady-state window sum-of-squares
     real* pv_s = wsteady + hop;                                        // 8 params
+    real2* w2s = reinterpret_cast<real2*>(pv_s + 8);                   // M window pairs (w[2m], w[2m+1])
+    real2* tws = w2s + M;                                              // M/2 twiddles W_M^k of the half-size FFT
     const int tid = threadIdx.x;
     const int item = a.item0 + blockIdx.x;
     const int u = item / a.n_params, c = item - u * a.n_params;
@@ -189,6 +191,8 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (LOG2N >= 10 ? 3 : 4)) 
         pv_s[tid] = v;
     }
     for (int i = tid; i < W; i += NT) ring[i] = R(0);
+    for (int m = tid; m < M; m += NT) w2s[m] = mk2(w[2 * m], w[2 * m + 1]);
+    load_twiddles<M>(tws, a.T->tw, tid, NT);
     for (int r = tid; r < hop; r += NT) {
         real s = R(0);
         for (int n = r; n < NFFT; n += hop) s = r_fma(w[n], w[n], s);
@@ -197,9 +201,7 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (LOG2N >= 10 ? 3 : 4)) 
     __syncthreads();
     if (ALG == 3 && tid == 0) pv_s[6] = r_log(pv_s[2]) * CSE_LOG2E;     // log2(gain_floor)
     __syncthreads();
-    real pv[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) pv[i] = pv_s[i];
+    const real* pv = pv_s;                   // parameters stay in shared memory (broadcast reads) to save registers
     const real mu_raw = (ALG == 2) ? (real)a.params[c].v[4] : (ALG == 3) ? (real)a.params[c].v[3] : R(-1);
     const bool smooth = (ALG >= 2) && a.noise_tv && (mu_raw >= R(0));
 
@@ -232,16 +234,39 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (LOG2N >= 10 ? 3 : 4)) 
 #pragma unroll
             for (int f = 0; f < F; ++f) {
                 const int t = t0 + f;
+                const int row = t * nbp;              // < 2^31: nf <= 8192 frames of <= 1032 bins
                 const bool on = i < n_slots && t < nf;
-                yv[i][0][f] = on ? Yu[(size_t)t * nbp + ka] : mk2(R(0), R(0));
-                nv[i][0][f] = on ? (a.noise_tv ? Nu[(size_t)t * nbp + ka] : nstat[i][0]) : R(1);
+                yv[i][0][f] = on ? Yu[row + ka] : mk2(R(0), R(0));
+                nv[i][0][f] = on ? (a.noise_tv ? Nu[row + ka] : nstat[i][0]) : R(1);
                 const bool onb = on && is_pair;
-                yv[i][1][f] = onb ? Yu[(size_t)t * nbp + kb] : mk2(R(0), R(0));
-                nv[i][1][f] = onb ? (a.noise_tv ? Nu[(size_t)t * nbp + kb] : nstat[i][1]) : R(1);
+                yv[i][1][f] = onb ? Yu[row + kb] : mk2(R(0), R(0));
+                nv[i][1][f] = onb ? (a.noise_tv ? Nu[row + kb] : nstat[i][1]) : R(1);
             }
         }
     };
     fetch(0);
+
+    // Overlap-add gather plan.  Thread owns window pair-positions jj = tid + k*NT; frame f of an
+    // iteration contributes its sample pair m = jj - f*hop/2 (if 0 <= m < M), which sits at a fixed
+    // shared-memory offset in the bit-reversed FFT output: all loop-invariant, computed once.
+    constexpr int KMAX = ((NFFT + (F - 1) * (NFFT / 2)) / 2 + NT - 1) / NT;
+    const int hh = hop >> 1;
+    unsigned zoff[KMAX][(F + 1) / 2];            // two 16-bit offsets per register; 0xffff = no contribution
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+        const int jj = tid + k * NT;
+#pragma unroll
+        for (int f2 = 0; f2 < (F + 1) / 2; ++f2) {
+            unsigned packed = 0;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int f = 2 * f2 + e, m = jj - f * hh;
+                const unsigned off = (f < F && jj < W / 2 && m >= 0 && m < M) ? (unsigned)(f * XST + SIDX(brev_n(m, LOG2M))) : 0xffffu;
+                packed |= off << (16 * e);
+            }
+            zoff[k][f2] = packed;
+        }
+    }
 
     const int total_pos = L + M;             // padded positions [0, L + M) must be emitted
     int ring_base = 0;                       // ring slot of padded position t0 * hop
@@ -276,28 +301,28 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (LOG2N >= 10 ? 3 : 4)) 
                     }
                 }
             }
-            fetch(t0 + F);                   // next iteration's spectra fly during the FFT
             __syncthreads();
-            fft_dif<LOG2M, true>(xs, F, XST, a.T->tw, tid, NT);
+            fft_dif<LOG2M, true, M>(xs, F, XST, tws, tid, NT);
+            fetch(t0 + F);                   // next iteration's spectra fly during the overlap-add (issued after
+                                             // the FFT so that they are not live across its register-hungry passes)
         }
         // overlap-add the F windowed frames two samples at a time (sample pair 2m,2m+1 of a frame
         // is one complex FFT output), emit the F*hop positions no later frame touches
         const int p_begin = t0 * hop;
         const int emit_end = p_begin + F * hop;
-        for (int jj = tid; jj < W / 2; jj += NT) {
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) {
+            const int jj = tid + k * NT;
+            if (jj >= W / 2) break;
             const int j = 2 * jj, p = p_begin + j;
             int slot = ring_base + j;
             if (slot >= W) slot -= W;
             real2 acc = *reinterpret_cast<real2*>(ring + slot);
-            if (any) {
+            if (any) {                       // frames beyond n_frames were written as zero spectra
 #pragma unroll
                 for (int f = 0; f < F; ++f) {
-                    const int n = j - f * hop;               // even sample index inside frame t0+f
-                    if (n >= 0 && n < NFFT && t0 + f < nf) {
-                        const real2 zz = xs[f * XST + SIDX(brev_n(n >> 1, LOG2M))];
-                        acc.x = r_fma(zz.x, w[n], acc.x);
-                        acc.y = r_fma(zz.y, w[n + 1], acc.y);
-                    }
+                    const unsigned off = (zoff[k][f >> 1] >> (16 * (f & 1))) & 0xffffu;
+                    if (off != 0xffffu) acc = cfma2(xs[off], w2s[jj - f * hh], acc);
                 }
             }
             if (p < emit_end) {
