@@ -52,7 +52,10 @@ CSE_D void dif_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
     constexpr int q = h >> (RL - 1);
     constexpr int per = N / NB;
     const int total = nbatch * per;
-    constexpr int twstep = (TWN / 2) / h;         // W_{2h}^p = W_T^{p * T/(2h)}, T = TWN = period of the table
+    // TWN > 0: `tw` is a flat table W_TWN^k.  TWN == 0: `tw` is the compact per-pass layout of
+    // load_pass_twiddles (block of this pass at 3(q-1)/7: [W_{8q}^j | W_{4q}^j | W_{2q}^j], unit stride).
+    constexpr int twstep = TWN > 0 ? (TWN / 2) / h : 0;
+    constexpr int coff = 3 * (q - 1) / 7;
     for (int idx = tid; idx < total; idx += nth) {
         const int b = idx / per, r = idx - b * per;
         const int j = r & (q - 1), grp = r / q;
@@ -63,7 +66,9 @@ CSE_D void dif_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
 #pragma unroll
         for (int m = 0; m < NB; ++m) v[m] = p[SIDX(m * q)];
         if (RL == 3) {
-            const real2 w1 = tw_load(tw, j * twstep), w2 = tw_load(tw, j * twstep * 2), w3 = tw_load(tw, j * twstep * 4);
+            const real2 w1 = TWN > 0 ? tw_load(tw, j * twstep) : tw_load(tw, coff + j);
+            const real2 w2 = TWN > 0 ? tw_load(tw, j * twstep * 2) : tw_load(tw, coff + q + j);
+            const real2 w3 = TWN > 0 ? tw_load(tw, j * twstep * 4) : tw_load(tw, coff + 2 * q + j);
             real2 d;
             d = csub(v[0], v[4]); v[0] = cadd(v[0], v[4]); v[4] = twmul<CONJ>(rotf<0, CONJ>(d), w1);
             d = csub(v[1], v[5]); v[1] = cadd(v[1], v[5]); v[5] = twmul<CONJ>(rotf<1, CONJ>(d), w1);
@@ -77,14 +82,15 @@ CSE_D void dif_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
 #pragma unroll
             for (int g = 0; g < 8; g += 2) { d = csub(v[g], v[g + 1]); v[g] = cadd(v[g], v[g + 1]); v[g + 1] = twmul<CONJ>(d, w3); }
         } else if (RL == 2) {
-            const real2 w1 = tw_load(tw, j * twstep), w2 = tw_load(tw, j * twstep * 2);
+            const real2 w1 = TWN > 0 ? tw_load(tw, j * twstep) : tw_load(tw, coff + j);
+            const real2 w2 = TWN > 0 ? tw_load(tw, j * twstep * 2) : tw_load(tw, coff + q + j);
             real2 d;
             d = csub(v[0], v[2]); v[0] = cadd(v[0], v[2]); v[2] = twmul<CONJ>(d, w1);
             d = csub(v[1], v[3]); v[1] = cadd(v[1], v[3]); v[3] = twmul<CONJ>(rotf<2, CONJ>(d), w1);
             d = csub(v[0], v[1]); v[0] = cadd(v[0], v[1]); v[1] = twmul<CONJ>(d, w2);
             d = csub(v[2], v[3]); v[2] = cadd(v[2], v[3]); v[3] = twmul<CONJ>(d, w2);
         } else {
-            const real2 w1 = tw_load(tw, j * twstep);
+            const real2 w1 = TWN > 0 ? tw_load(tw, j * twstep) : tw_load(tw, coff + j);
             real2 d = csub(v[0], v[1]); v[0] = cadd(v[0], v[1]); v[1] = twmul<CONJ>(d, w1);
         }
 #pragma unroll
@@ -100,7 +106,8 @@ CSE_D void dit_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
     constexpr int q = Q;
     constexpr int per = N / NB;
     const int total = nbatch * per;
-    constexpr int twq = (TWN / 2) / q;            // W_{2q}^p = W_T^{p * T/(2q)}
+    constexpr int twq = TWN > 0 ? (TWN / 2) / q : 0;     // W_{2q}^p = W_T^{p * T/(2q)}
+    constexpr int coff = 3 * (q - 1) / 7;                 // compact layout, see dif_pass
     for (int idx = tid; idx < total; idx += nth) {
         const int b = idx / per, r = idx - b * per;
         const int j = r & (q - 1), grp = r / q;
@@ -110,7 +117,9 @@ CSE_D void dit_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
         for (int m = 0; m < NB; ++m) v[m] = p[SIDX(m * q)];
         if (RL == 3) {
             // distances q (W_{2q}^j), 2q (W_{4q}^{j + (m&1)q}), 4q (W_{8q}^{j + (m&3)q}); conjugated
-            const real2 w3 = tw_load(tw, j * twq), w2 = tw_load(tw, j * (twq >> 1)), w1 = tw_load(tw, j * (twq >> 2));
+            const real2 w3 = TWN > 0 ? tw_load(tw, j * twq) : tw_load(tw, coff + 2 * q + j);
+            const real2 w2 = TWN > 0 ? tw_load(tw, j * (twq >> 1)) : tw_load(tw, coff + q + j);
+            const real2 w1 = TWN > 0 ? tw_load(tw, j * (twq >> 2)) : tw_load(tw, coff + j);
             real2 t;
 #pragma unroll
             for (int g = 0; g < 8; g += 2) { t = twmul<CONJ>(v[g + 1], w3); v[g + 1] = csub(v[g], t); v[g] = cadd(v[g], t); }
@@ -124,14 +133,15 @@ CSE_D void dit_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
             t = rotf<2, CONJ>(twmul<CONJ>(v[6], w1)); v[6] = csub(v[2], t); v[2] = cadd(v[2], t);
             t = rotf<3, CONJ>(twmul<CONJ>(v[7], w1)); v[7] = csub(v[3], t); v[3] = cadd(v[3], t);
         } else if (RL == 2) {
-            const real2 w2 = tw_load(tw, j * twq), w1 = tw_load(tw, j * (twq >> 1));
+            const real2 w2 = TWN > 0 ? tw_load(tw, j * twq) : tw_load(tw, coff + q + j);
+            const real2 w1 = TWN > 0 ? tw_load(tw, j * (twq >> 1)) : tw_load(tw, coff + j);
             real2 t;
             t = twmul<CONJ>(v[1], w2); v[1] = csub(v[0], t); v[0] = cadd(v[0], t);
             t = twmul<CONJ>(v[3], w2); v[3] = csub(v[2], t); v[2] = cadd(v[2], t);
             t = twmul<CONJ>(v[2], w1); v[2] = csub(v[0], t); v[0] = cadd(v[0], t);
             t = rotf<2, CONJ>(twmul<CONJ>(v[3], w1)); v[3] = csub(v[1], t); v[1] = cadd(v[1], t);
         } else {
-            const real2 w1 = tw_load(tw, j * twq);
+            const real2 w1 = TWN > 0 ? tw_load(tw, j * twq) : tw_load(tw, coff + j);
             real2 t = twmul<CONJ>(v[1], w1); v[1] = csub(v[0], t); v[0] = cadd(v[0], t);
         }
 #pragma unroll
@@ -143,36 +153,70 @@ CSE_D void dit_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
 // (e^-j); INV=true: unnormalised inverse (e^+j).  Ends with a __syncthreads().  Stage sizes are
 // template constants so that all index arithmetic folds to shifts and masks.
 template <int LOG2N, bool INV, int TWN = CSE_TW_N>
-CSE_D void fft_dif(real2* s, int nbatch, int bstride, const real2* __restrict__ tw, int tid, int nth) {
+CSE_D void fft_dif(real2* s, int nbatch, int bstride, const real2* __restrict__ tw, int tid, int nth,
+                   const real2* __restrict__ twg = nullptr) {
     constexpr int REM = LOG2N % 3, NP = LOG2N / 3;
     constexpr int H0 = 1 << (LOG2N - 1), H1 = H0 >> REM;
-    if constexpr (REM == 1) { dif_pass<LOG2N, 1, INV, H0, TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
-    if constexpr (REM == 2) { dif_pass<LOG2N, 2, INV, H0, TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
-    if constexpr (NP >= 1) { dif_pass<LOG2N, 3, INV, H1, TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
-    if constexpr (NP >= 2) { dif_pass<LOG2N, 3, INV, (H1 >> 3), TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
-    if constexpr (NP >= 3) { dif_pass<LOG2N, 3, INV, (H1 >> 6), TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
-    if constexpr (NP >= 4) { dif_pass<LOG2N, 3, INV, (H1 >> 9), TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    constexpr int TWR = TWN < 0 ? CSE_TW_N : TWN;          // remainder pass: flat global table when TWN == -1
+    constexpr int TW3 = TWN < 0 ? 0 : TWN;                 // radix-8 passes: compact when TWN <= 0
+    const real2* twr = TWN < 0 ? twg : tw;
+    if constexpr (REM == 1) { dif_pass<LOG2N, 1, INV, H0, TWR>(s, nbatch, bstride, twr, tid, nth); __syncthreads(); }
+    if constexpr (REM == 2) { dif_pass<LOG2N, 2, INV, H0, TWR>(s, nbatch, bstride, twr, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 1) { dif_pass<LOG2N, 3, INV, H1, TW3>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 2) { dif_pass<LOG2N, 3, INV, (H1 >> 3), TW3>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 3) { dif_pass<LOG2N, 3, INV, (H1 >> 6), TW3>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 4) { dif_pass<LOG2N, 3, INV, (H1 >> 9), TW3>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
 }
 
 // Decimation-in-time transform, bit-reversed in -> natural-order out.  Ends with a __syncthreads().
 template <int LOG2N, bool INV, int TWN = CSE_TW_N>
-CSE_D void fft_dit(real2* s, int nbatch, int bstride, const real2* __restrict__ tw, int tid, int nth) {
+CSE_D void fft_dit(real2* s, int nbatch, int bstride, const real2* __restrict__ tw, int tid, int nth,
+                   const real2* __restrict__ twg = nullptr) {
     constexpr int REM = LOG2N % 3, NP = LOG2N / 3;
-    if constexpr (NP >= 1) { dit_pass<LOG2N, 3, INV, 1, TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
-    if constexpr (NP >= 2) { dit_pass<LOG2N, 3, INV, 8, TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
-    if constexpr (NP >= 3) { dit_pass<LOG2N, 3, INV, 64, TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
-    if constexpr (NP >= 4) { dit_pass<LOG2N, 3, INV, 512, TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    constexpr int TWR = TWN < 0 ? CSE_TW_N : TWN;
+    constexpr int TW3 = TWN < 0 ? 0 : TWN;
+    const real2* twr = TWN < 0 ? twg : tw;
+    if constexpr (NP >= 1) { dit_pass<LOG2N, 3, INV, 1, TW3>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 2) { dit_pass<LOG2N, 3, INV, 8, TW3>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 3) { dit_pass<LOG2N, 3, INV, 64, TW3>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 4) { dit_pass<LOG2N, 3, INV, 512, TW3>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
     constexpr int QR = 1 << (3 * NP);
-    if constexpr (REM == 2) { dit_pass<LOG2N, 2, INV, QR, TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
-    if constexpr (REM == 1) { dit_pass<LOG2N, 1, INV, QR, TWN>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (REM == 2) { dit_pass<LOG2N, 2, INV, QR, TWR>(s, nbatch, bstride, twr, tid, nth); __syncthreads(); }
+    if constexpr (REM == 1) { dit_pass<LOG2N, 1, INV, QR, TWR>(s, nbatch, bstride, twr, tid, nth); __syncthreads(); }
 }
 
-// Compact twiddle table W_N^k, k < N/2, copied from the global W_8192 table into shared memory: a
-// warp's twiddle reads in the wide-stride passes would otherwise touch up to 32 different
-// 128-byte lines of the global table per instruction (profiles/r01e: L1TEX 71 % busy).
-template <int N>
-CSE_D void load_twiddles(real2* dst, const real2* __restrict__ tw_global, int tid, int nth) {
-    for (int k = tid; k < N / 2; k += nth) dst[k] = tw_global[k * (CSE_TW_N / N)];
+// Compact per-pass twiddle layout in shared memory (TWN == 0 / -1 above).  For every radix-8 pass
+// with smallest butterfly distance q (a power of 8) a block at offset 3(q-1)/7 holds
+// [W_{8q}^j | W_{4q}^j | W_{2q}^j], j < q, so that a warp's twiddle reads are unit-stride.  The
+// remainder pass (radix 2 or 4, q = 8^(LOG2N/3)) gets [W_{2q}^j] or [W_{4q}^j | W_{2q}^j] behind them
+// unless WITH_REM is false.  Reading the flat global W_8192 table instead costs up to 32 different
+// 128-byte lines per warp instruction in the narrow passes (profiles/r01e: L1TEX 71 % busy) and a
+// flat shared copy costs 2- to 8-way bank conflicts (profiles/r01f).
+template <int LOG2N, bool WITH_REM>
+struct FftTwLayout {
+    static constexpr int NP = LOG2N / 3, REM = LOG2N % 3;
+    static constexpr int QR = 1 << (3 * NP);
+    static constexpr int OFFR = 3 * (QR - 1) / 7;
+    static constexpr int SIZE = OFFR + (WITH_REM ? REM * QR : 0);
+};
+template <int LOG2N, bool WITH_REM>
+CSE_D void load_pass_twiddles(real2* dst, const real2* __restrict__ twg, int tid, int nth) {
+    typedef FftTwLayout<LOG2N, WITH_REM> LY;
+    for (int i = tid; i < LY::SIZE; i += nth) {
+        int idx;
+        if (i < LY::OFFR) {
+            // find the block: q = 8^k with 3(q-1)/7 <= i < 3(8q-1)/7
+            int q = 1, off = 0;
+            while (i >= off + 3 * q) { off += 3 * q; q <<= 3; }
+            const int r = i - off, which = r / q, j = r - which * q;          // which: 0 -> W_{8q}, 1 -> W_{4q}, 2 -> W_{2q}
+            idx = j * ((CSE_TW_N / 8) / q << which);
+        } else {
+            const int r = i - LY::OFFR, which = r / LY::QR, j = r - which * LY::QR;
+            // REM == 1: W_{2q}^j.  REM == 2: [W_{4q}^j | W_{2q}^j]
+            idx = LY::REM == 1 ? j * ((CSE_TW_N / 2) / LY::QR) : j * ((CSE_TW_N / 4) / LY::QR << which);
+        }
+        dst[i] = twg[idx];
+    }
 }
 
 CSE_D int brev_n(int k, int log2n) { return (int)(__brev((unsigned)k) >> (32 - log2n)); }

@@ -74,11 +74,11 @@ extern "C" int cse_noise_mintrack(const void* P, int n_utts, int n_frames, int n
 }
 
 // ------------------------------------------------------------------ K5 scoring
-static size_t align_smem() { return (size_t)(CSE_FFT_STRIDE(CSE_CORR_P) + CSE_CORR_P / 2) * sizeof(real2) + 48 * sizeof(double); }
+static size_t align_smem() { return (size_t)(CSE_FFT_STRIDE(CSE_CORR_P) + FftTwLayout<CSE_CORR_LOG2P, false>::SIZE + 2) * sizeof(real2) + 48 * sizeof(double); }
 static size_t stoi_smem(const ScoreGeom& g) {
     return 40 * sizeof(double) + sizeof(real) * ((size_t)CSE_STOI_T * CSE_FFT_STRIDE(256) * 2 +
                                                  (size_t)CSE_STOI_T * (CSE_STOI_K1 - CSE_STOI_K0) +
-                                                 (size_t)2 * CSE_NBANDS * (g.nfrm + 1) + 256 + 256) + sizeof(int) * (size_t)(g.nfr + 2);
+                                                 (size_t)2 * CSE_NBANDS * (g.nfrm + 1) + 256 + 320) + sizeof(int) * (size_t)(g.nfr + 2);
 }
 static size_t up64(size_t x) { return (x + 63) & ~(size_t)63; }
 static int check_sr(int sr) {

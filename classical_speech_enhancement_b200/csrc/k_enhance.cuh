@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (LOG2N >= 10 ? 3 : 4)) 
     real* wsteady = ring + W;                                          // hop: steady-state window sum-of-squares
     real* pv_s = wsteady + hop;                                        // 8 params
     real2* w2s = reinterpret_cast<real2*>(pv_s + 8);                   // M window pairs (w[2m], w[2m+1])
-    real2* tws = w2s + M;                                              // M/2 twiddles W_M^k of the half-size FFT
+    real2* tws = w2s + M;                                              // per-pass twiddles of the half-size FFT (FftTwLayout)
     const int tid = threadIdx.x;
     const int item = a.item0 + blockIdx.x;
     const int u = item / a.n_params, c = item - u * a.n_params;
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (LOG2N >= 10 ? 3 : 4)) 
     }
     for (int i = tid; i < W; i += NT) ring[i] = R(0);
     for (int m = tid; m < M; m += NT) w2s[m] = mk2(w[2 * m], w[2 * m + 1]);
-    load_twiddles<M>(tws, a.T->tw, tid, NT);
+    load_pass_twiddles<LOG2M, true>(tws, a.T->tw, tid, NT);
     for (int r = tid; r < hop; r += NT) {
         real s = R(0);
         for (int n = r; n < NFFT; n += hop) s = r_fma(w[n], w[n], s);
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (LOG2N >= 10 ? 3 : 4)) 
                 }
             }
             __syncthreads();
-            fft_dif<LOG2M, true, M>(xs, F, XST, tws, tid, NT);
+            fft_dif<LOG2M, true, 0>(xs, F, XST, tws, tid, NT);
             fetch(t0 + F);                   // next iteration's spectra fly during the overlap-add (issued after
                                              // the FFT so that they are not live across its register-hungry passes)
         }

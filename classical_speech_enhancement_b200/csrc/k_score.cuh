@@ -152,8 +152,8 @@ __global__ void __launch_bounds__(512, 2) align_kernel(ScoreArgs a) {
     constexpr int P = CSE_CORR_P, NT = 512, PER = P / NT, M = CSE_MAXLAG, B = CSE_CORR_B;
     CSE_DYN_SMEM(smem_raw);
     real2* z = reinterpret_cast<real2*>(smem_raw);                              // CSE_FFT_STRIDE(P)
-    real2* tws = z + CSE_FFT_STRIDE(P);                                         // P/2 twiddles W_P^k
-    double* scratch = reinterpret_cast<double*>(tws + P / 2);                   // 40 doubles
+    real2* tws = z + CSE_FFT_STRIDE(P);                                         // radix-8 pass twiddles (the radix-2 pass reads the global table, unit stride)
+    double* scratch = reinterpret_cast<double*>(tws + FftTwLayout<CSE_CORR_LOG2P, false>::SIZE + 1);                   // 40 doubles
     const int tid = threadIdx.x, li = blockIdx.x, item = a.item0 + li;
     const int u = CLEAN ? item : item / a.per_utt;
     const ScoreGeom& g = a.g;
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(512, 2) align_kernel(ScoreArgs a) {
 
     // mean over the correlation window; a non-finite sample there makes the reference's whole
     // correlation NaN, and np.argmax of an all-NaN array is index 0, i.e. lag = -max_lag
-    load_twiddles<P>(tws, a.T->tw, tid, NT);
+    load_pass_twiddles<CSE_CORR_LOG2P, false>(tws, a.T->tw, tid, NT);
     double s = 0.0, e2 = 0.0;
     int bad = 0;
     for (int i = tid; i < (CLEAN ? L : Nc); i += NT) {
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(512, 2) align_kernel(ScoreArgs a) {
             z[SIDX(idx)] = mk2(re, im);
         }
         __syncthreads();
-        fft_dif<CSE_CORR_LOG2P, false, P>(z, 1, 0, tws, tid, NT);
+        fft_dif<CSE_CORR_LOG2P, false, -1>(z, 1, 0, tws, tid, NT, a.T->tw);
         if (CLEAN) {
             for (int idx = tid; idx < P; idx += NT) Q[(size_t)pair * P + idx] = z[SIDX(idx)];
         } else {
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(512, 2) align_kernel(ScoreArgs a) {
 #pragma unroll
     for (int k = 0; k < PER; ++k) z[SIDX(tid + k * NT)] = acc[k];
     __syncthreads();
-    fft_dit<CSE_CORR_LOG2P, true, P>(z, 1, 0, tws, tid, NT);
+    fft_dit<CSE_CORR_LOG2P, true, -1>(z, 1, 0, tws, tid, NT, a.T->tw);
     // first maximum over k = -maxlag .. maxlag
     const real invP = R(1) / (real)P;
     real best = -cse_inf();
@@ -454,11 +454,11 @@ __global__ void __launch_bounds__(256, 4) stoi_kernel(ScoreArgs a, const double*
     real* ytob = pw + T * NK;                                                 // 15 * Kf
     real* xtob = ytob + CSE_NBANDS * (g.nfrm + 1);                            // 15 * Kf (MODE 0)
     real* w_s = xtob + CSE_NBANDS * (g.nfrm + 1);                             // 256: np.hanning(258)[1:-1]
-    real2* tws = reinterpret_cast<real2*>(w_s + 256);                         // 128 twiddles W_256^k
-    int* kept_s = reinterpret_cast<int*>(tws + 128);                          // nfr + 2 kept-frame indices
+    real2* tws = reinterpret_cast<real2*>(w_s + 256);                         // per-pass twiddles of the 256-point FFT
+    int* kept_s = reinterpret_cast<int*>(tws + 160);                          // nfr + 2 kept-frame indices
 
     for (int i = tid; i < 256; i += NT) w_s[i] = a.T->stoi_win[i];
-    load_twiddles<256>(tws, a.T->tw, tid, NT);
+    load_pass_twiddles<8, true>(tws, a.T->tw, tid, NT);
     for (int i = tid; i < K; i += NT) kept_s[i] = kept[i];
     __syncthreads();
     const real* __restrict__ sig = a.wav + (size_t)li * g.L;
@@ -550,7 +550,7 @@ __global__ void __launch_bounds__(256, 4) stoi_kernel(ScoreArgs a, const double*
             }
         }
         __syncthreads();
-        fft_dif<8, false, 256>(fbuf, T, BST, tws, tid, NT);
+        fft_dif<8, false, 0>(fbuf, T, BST, tws, tid, NT);
         for (int idx = tid; idx < T * NK; idx += NT) {
             const int f = idx / NK, k = CSE_STOI_K0 + (idx - f * NK);
             const real2* zf = fbuf + f * BST;
