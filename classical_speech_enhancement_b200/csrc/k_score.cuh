@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(256, 4) stoi_kernel(ScoreArgs a, const double*
         // clean side: envelopes + per (segment, band) norm, mean, 1/(centred norm + EPS)
         for (int i = tid; i < CSE_NBANDS * Kf; i += NT) xtob_c[i] = ytob[i];
         for (int idx = tid; idx < J * CSE_NBANDS; idx += NT) {
-            const int j = idx / CSE_NBANDS, b = idx - j * CSE_NBANDS;
+            const int b = idx / J, j = idx - b * J;        // segment index fastest: a warp reads consecutive envelopes
             const real* x = ytob + b * Kf + j;
             real s1 = R(0), s2 = R(0);
             for (int n = 0; n < CSE_NSEG; ++n) { s1 += x[n]; s2 = r_fma(x[n], x[n], s2); }
@@ -594,7 +594,7 @@ __global__ void __launch_bounds__(256, 4) stoi_kernel(ScoreArgs a, const double*
     const real clipc = R(1) + R(5.623413251903491);
     real dsum = R(0);
     for (int idx = tid; idx < J * CSE_NBANDS; idx += NT) {
-        const int j = idx / CSE_NBANDS, b = idx - j * CSE_NBANDS;
+        const int b = idx / J, j = idx - b * J;            // (band, segment), segment fastest: conflict-free, coalesced
         const real* x = xtob + b * Kf + j;
         const real* y = ytob + b * Kf + j;
         const real xn = seg_c[idx], xmean = seg_c[(size_t)J * CSE_NBANDS + idx], xinv = seg_c[(size_t)2 * J * CSE_NBANDS + idx];
