@@ -233,7 +233,7 @@ def main():
     import torch
     import torch.distributed as dist
     from classical_speech_enhancement_b200 import sweep as sw
-    from classical_speech_enhancement_b200.distributed import gather_scores, shard_bounds
+    from classical_speech_enhancement_b200.distributed import gather_device_scores, shard_bounds
     from classical_speech_enhancement_b200.engine import SweepEngine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -263,13 +263,12 @@ def main():
     # ---------------- device-resident arm: inputs already in HBM
     eng = SweepEngine(clean_pin.numpy(), noisy_pin.numpy(), chunk_items=args.chunk)
 
+    u_pad = max(b[r + 1] - b[r] for r in range(world))
+
     def step_resident():
         eng.reset()
-        scores, _, _ = sw.run_engine(eng)
-        if world > 1:
-            for name in scores:
-                gather_scores(scores[name], args.utts, device=device)
-        return scores
+        items = sw.run_engine_device(eng, u_pad=u_pad)
+        return gather_device_scores(eng, items, args.utts, device=device)   # NCCL all_gather (N>1) + D2H + expansion
 
     for _ in range(args.warmup):
         step_resident()
@@ -299,11 +298,10 @@ def main():
 
     # ---------------- end-to-end arm: host buffers in, host score tables out, every step
     def step_e2e():
-        out = sw.sweep_dataset(clean_pin.numpy(), noisy_pin.numpy(), select=False, chunk_items=args.chunk)
-        if world > 1:
-            for name in out["scores"]:
-                gather_scores(out["scores"][name], args.utts, device=device)
-        return out
+        # host buffers in (pinned), host score tables out: the public dataset-level path
+        e = SweepEngine(clean_pin.numpy(), noisy_pin.numpy(), chunk_items=args.chunk)
+        items = sw.run_engine_device(e, u_pad=u_pad)
+        return e, gather_device_scores(e, items, args.utts, device=device)
 
     del eng
     torch.cuda.empty_cache()
@@ -312,14 +310,14 @@ def main():
     e2e_steps = max(1, min(args.steps, 2))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        out = step_e2e()
+        e2e_eng, e2e_scores = step_e2e()
     barrier()
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te[0]) / e2e_steps
-    h2d = out["engine"].h2d_bytes
-    d2h = sum(v.nbytes for v in out["scores"].values())
+    h2d = e2e_eng.h2d_bytes
+    d2h = args.utts * nominal_points * e2e_eng.lib.score_dtype.itemsize    # the (gathered) nominal score tables, per rank
 
     # ---------------- roofline of the dominant kernel (events around every chunk launch, timed steps only)
     names = {0: "ss", 1: "wiener", 2: "mmse", 3: "omlsa"}

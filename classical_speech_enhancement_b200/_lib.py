@@ -44,6 +44,7 @@ SIGNATURES = {
     "cse_score_items": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "cse_align_items": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "cse_stoi_items": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "cse_expand_scores": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "cse_debug_special": (_i, [_i, _vp, _vp, _i]),
     "cse_sweep": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
 }

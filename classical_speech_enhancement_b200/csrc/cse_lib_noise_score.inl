@@ -233,6 +233,26 @@ extern "C" int cse_stoi_items(const void* tables, const void* wav, int item0, in
     return score_items(tables, wav, item0, n_items, per_utt, length, clean, cache, finalize, scores, workspace, stream, 2);
 }
 
+// ------------------------------------------------------------------ nominal score table
+// Broadcast of the unique candidates' scores to every nominal grid point (duplicates through dead
+// parameters get the identical record, as the reference would compute them), on the device:
+// out[u][p] = unique[base[p] + u * stride[p]]  (16-byte records; one thread per record).
+__global__ void __launch_bounds__(256) expand_scores_kernel(const cse_score_t* __restrict__ uniq, const int* __restrict__ base,
+                                                            const int* __restrict__ stride, int n_utts, int n_points,
+                                                            cse_score_t* __restrict__ out) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x, u = blockIdx.y;
+    if (p < n_points && u < n_utts) out[(size_t)u * n_points + p] = uniq[(size_t)base[p] + (size_t)u * stride[p]];
+}
+
+extern "C" int cse_expand_scores(const cse_score_t* unique_scores, const int* base, const int* stride, int n_utts,
+                                 int n_points, cse_score_t* out, void* stream) {
+    CSE_REQUIRE(unique_scores && base && stride && out, "NULL argument");
+    CSE_REQUIRE(n_utts > 0 && n_points > 0, "bad sizes");
+    CSE_LAUNCH(expand_scores_kernel, dim3((n_points + 255) / 256, n_utts), 256, 0, stream, unique_scores, base, stride,
+               n_utts, n_points, out);
+    return check_launch("expand_scores");
+}
+
 // ------------------------------------------------------------------ host-side probes for tests
 // Evaluates the gain rules' special-function fits on the host (same code the kernels inline).
 extern "C" int cse_debug_special(int which, const double* x, double* y, int n) {

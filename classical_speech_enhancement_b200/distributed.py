@@ -55,18 +55,52 @@ def gather_scores(local, n_utts, device=None):
     return out
 
 
+def gather_device_scores(engine, items, n_utts, device=None):
+    """all_gather of the per-algorithm nominal device tables [u_pad][points] (no host staging on the
+    way in), one device->host copy, and views per rank block.  `items` is the list returned by
+    sweep.run_engine_device with u_pad = the largest shard."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    b = shard_bounds(n_utts, world)
+    scores = {}
+    for name, pts, buf, pl in items:
+        if world == 1:
+            scores[name] = engine.table_to_host(engine.be.view_bytes_as(buf, np.uint8), pl, engine.U)
+            continue
+        send = buf if isinstance(buf, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(buf))
+        recv = torch.empty((world,) + tuple(send.shape), dtype=torch.uint8, device=send.device)
+        if send.is_cuda:
+            dist.all_gather_into_tensor(recv, send)
+        else:
+            dist.all_gather(list(recv.unbind(0)), send)
+        host = recv.cpu().numpy()
+        if all(b[r + 1] - b[r] == b[1] - b[0] for r in range(world)):
+            scores[name] = host.reshape(-1).view(engine.lib.score_dtype).reshape(n_utts, pl["n_points"])   # zero copy
+        else:
+            scores[name] = np.concatenate([engine.table_to_host(host[r], pl, b[r + 1] - b[r]) for r in range(world)])
+    return scores
+
+
 def sweep_sharded(clean, noisy, grids=None, select=True, chunk_items=4736, device=None, engine_kwargs=None):
     """Each rank sweeps its block of utterances; every rank returns the full gathered tables.
     ``clean`` / ``noisy`` are the full host arrays [U, L] (each rank slices its block)."""
     import torch.distributed as dist
     from . import sweep as sw
+    from .engine import SweepEngine
     grids = grids or sw.DEFAULT_GRIDS
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
-    sl = local_slice(clean.shape[0], rank, world)
-    local = sw.sweep_dataset(clean[sl], noisy[sl], grids=grids, select=False, chunk_items=chunk_items,
-                             engine_kwargs=engine_kwargs)
-    scores = {name: gather_scores(sc, clean.shape[0], device=device) for name, sc in local["scores"].items()}
-    return {"scores": scores, "points": local["points"],
-            "selection": sw.select_all(scores, local["points"]) if select else None,
-            "local_engine": local["engine"]}
+    n_utts = clean.shape[0]
+    if n_utts < world:
+        raise ValueError(f"{n_utts} utterances cannot be sharded over {world} ranks")
+    b = shard_bounds(n_utts, world)
+    u_pad = max(b[r + 1] - b[r] for r in range(world))
+    sl = slice(b[rank], b[rank + 1])
+    eng = SweepEngine(clean[sl], noisy[sl], chunk_items=chunk_items, **(engine_kwargs or {}))
+    items = sw.run_engine_device(eng, grids, u_pad=u_pad)
+    scores = gather_device_scores(eng, items, n_utts, device=device)
+    points = {name: pts for name, pts, _, _ in items}
+    return {"scores": scores, "points": points,
+            "selection": sw.select_all(scores, points) if select else None,
+            "local_engine": eng}

@@ -25,6 +25,7 @@ SR = 16000
 #: changes it (-> libcse_sm100a.so + CUDA tensors); the CPU test-suite points it at the
 #: thread-emulated build to exercise the host logic without a GPU.
 _runtime = {"lib": None, "backend_factory": None}
+_PLAN_CACHE = {}
 
 
 def configure_runtime(lib=None, backend_factory=None):
@@ -61,6 +62,9 @@ class TorchCudaBackend:
 
     def ptr(self, buf):
         return None if buf is None else ctypes.c_void_p(buf.data_ptr())
+
+    def ptr_at(self, buf, byte_offset):
+        return ctypes.c_void_p(buf.data_ptr() + int(byte_offset))
 
     def stream(self):
         return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
@@ -106,6 +110,7 @@ class SweepEngine:
         self._stft = {}
         self._noise = {}
         self._ws = {}
+        self._plans = {}
         self.launches = 0
         self.cache = None
         self.sr = sr
@@ -225,29 +230,56 @@ class SweepEngine:
         self._noise.clear()
 
     # ------------------------------------------------------------------ the sweep
-    def sweep(self, alg_name, points):
-        """Scores of every grid point for every utterance.
-
-        Returns a structured array [U, len(points)] (stoi, snr, lag, flags) in the reference's
-        grid order.  Points that differ only in dead parameters are computed once and their
-        score broadcast (the reference would produce bit-identical duplicates).  ``unique`` is
-        recorded in ``self.last_unique``.
-        """
-        alg = ALGORITHM_IDS[alg_name] if isinstance(alg_name, str) else int(alg_name)
+    def _plan(self, alg, points):
+        """Grouped / deduplicated launch plan of a grid, cached per (algorithm, points list, length):
+        host-only data shared by every engine of the process; device-side maps are per engine."""
+        key = (alg, id(points), len(points), self.L)
+        hit = _PLAN_CACHE.get(key)
+        if hit is not None and hit[0] is points:
+            pl = self._plans.get(key)
+            if pl is None:
+                pl = dict(hit[1])
+                self._plans[key] = pl
+            return pl
         groups = plan(alg, points, self.n_frames)
-        out = np.zeros((self.U, len(points)), dtype=self.lib.score_dtype)
-        pending = []
-        unique = 0
+        info, col = [], 0
+        for gkey, g in groups.items():
+            n_rows = len(g["rows"])
+            member_idx = np.concatenate([np.asarray(m, dtype=np.int64) for m in g["members"]])
+            row_idx = np.concatenate([np.full(len(m), r, dtype=np.int64) for r, m in enumerate(g["members"])])
+            info.append({"key": gkey, "rows": g["rows"], "params_host": _lib.pack_params(g["rows"]), "n_rows": n_rows,
+                         "col0": col, "member_idx": member_idx, "row_idx": row_idx})
+            col += n_rows
+        out = {"groups": info, "unique": col, "n_points": len(points)}
+        _PLAN_CACHE[key] = (points, out)
+        pl = dict(out)
+        self._plans[key] = pl
+        return pl
+
+    def sweep_device(self, alg_name, points, u_pad=None):
+        """Enqueue the whole sweep of one algorithm; returns (device table, plan).
+
+        The device table is the NOMINAL score table [u_pad][n_points] of 16-byte records (u_pad >= U
+        rows so that equally sized tables can be all-gathered across ranks; rows >= U are zero).
+        Unique candidates are scored once into a scratch buffer and broadcast to their duplicates by
+        ``cse_expand_scores``; nothing is synchronised or copied to the host here."""
+        alg = ALGORITHM_IDS[alg_name] if isinstance(alg_name, str) else int(alg_name)
+        pl = self._plan(alg, points)
+        u_pad = self.U if u_pad is None else int(u_pad)
         be, lib_ = self.be, self.lib
-        for key, g in groups.items():
+        rec = self.lib.score_dtype.itemsize
+        uniq = be.empty((max(1, self.U * pl["unique"] * rec),), np.uint8)
+        keep = []
+        for g in pl["groups"]:
+            key = g["key"]
             n_fft, hop = key[0], key[1]
             Y = self.stft(n_fft, hop)
             N, tv = self.noise(key)
-            rows = g["rows"]
-            unique += len(rows)
-            params = be.from_host(_lib.pack_params(rows))
-            scores = be.empty((self.U * len(rows) * self.lib.score_dtype.itemsize,), np.uint8)
-            total = self.U * len(rows)
+            n_rows = g["n_rows"]
+            params = be.from_host(g["params_host"])
+            keep.append(params)
+            sc_ptr = be.ptr_at(uniq, self.U * g["col0"] * rec)          # group block [U][n_rows]
+            total = self.U * n_rows
             chunk = min(self.chunk_items, total)
             wav = self._workspace("wav", chunk * self.L * np.dtype(self.real).itemsize)
             nbytes = lib_.score_workspace_bytes(chunk, self.L, SR)
@@ -256,10 +288,10 @@ class SweepEngine:
                 n = min(chunk, total - i0)
                 t0 = self._tick()
                 lib_.enhance_items(be.ptr(self.tables), alg, be.ptr(Y), be.ptr(N), int(tv), self.L, n_fft, hop,
-                                   be.ptr(params), len(rows), i0, n, be.ptr(wav), be.stream())
+                                   be.ptr(params), n_rows, i0, n, be.ptr(wav), be.stream())
                 t1 = self._tick()
-                sargs = (be.ptr(self.tables), be.ptr(wav), i0, n, len(rows), self.L, SR, be.ptr(self.clean),
-                         be.ptr(self.cache), 1, be.ptr(scores), be.ptr(ws), nbytes, be.stream())
+                sargs = (be.ptr(self.tables), be.ptr(wav), i0, n, n_rows, self.L, SR, be.ptr(self.clean),
+                         be.ptr(self.cache), 1, sc_ptr, be.ptr(ws), nbytes, be.stream())
                 lib_.align_items(*sargs)
                 t2 = self._tick()
                 lib_.stoi_items(*sargs)
@@ -268,13 +300,36 @@ class SweepEngine:
                 self._record(("align", alg, n_fft, hop, key[2]), n, t1, t2)
                 self._record(("stoi", alg, n_fft, hop, key[2]), n, t2, t3)
                 self.launches += 3
-            pending.append((g, scores, params))
-        for g, scores, _ in pending:
-            sc = be.view_bytes_as(scores, self.lib.score_dtype).reshape(self.U, len(g["rows"]))
-            for r, members in enumerate(g["members"]):
-                out[:, members] = sc[:, r:r + 1]
-        self.last_unique = unique
-        return out
+        table = (be.zeros if u_pad > self.U else be.empty)((u_pad * pl["n_points"] * rec,), np.uint8)
+        if "dev_maps" not in pl or pl["dev_maps"][0] != self.U:
+            base = np.zeros(pl["n_points"], dtype=np.int32)
+            stride = np.zeros(pl["n_points"], dtype=np.int32)
+            for g in pl["groups"]:
+                base[g["member_idx"]] = self.U * g["col0"] + g["row_idx"]
+                stride[g["member_idx"]] = g["n_rows"]
+            pl["dev_maps"] = (self.U, be.from_host(base), be.from_host(stride))
+        _, dbase, dstride = pl["dev_maps"]
+        lib_.expand_scores(be.ptr(uniq), be.ptr(dbase), be.ptr(dstride), self.U, pl["n_points"], be.ptr(table), be.stream())
+        self.launches += 1
+        self._keepalive = (keep, uniq)  # must outlive the enqueued kernels
+        self.last_unique = pl["unique"]
+        return table, pl
+
+    def table_to_host(self, raw_bytes, pl, u_rows):
+        """[u_pad][n_points] record bytes -> structured array [u_rows, n_points]."""
+        dt = self.lib.score_dtype
+        return np.asarray(raw_bytes).reshape(-1).view(dt).reshape(-1, pl["n_points"])[:u_rows]
+
+    def sweep(self, alg_name, points):
+        """Scores of every grid point for every utterance.
+
+        Returns a structured array [U, len(points)] (stoi, snr, lag, flags) in the reference's
+        grid order.  Points that differ only in dead parameters are computed once and their
+        score broadcast (the reference would produce bit-identical duplicates).  ``unique`` is
+        recorded in ``self.last_unique``.
+        """
+        table, pl = self.sweep_device(alg_name, points)
+        return self.table_to_host(self.be.view_bytes_as(table, np.uint8), pl, self.U)
 
     def sweep_ranges(self, alg_name, param_ranges):
         points = grid_points(param_ranges)

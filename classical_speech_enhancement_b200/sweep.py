@@ -27,14 +27,36 @@ def nominal_and_unique(grids=DEFAULT_GRIDS):
     return nominal, unique
 
 
-def run_engine(engine, grids=DEFAULT_GRIDS):
-    """Device part only: {alg: structured scores [U, n_points]} (+ points)."""
-    scores, points, unique = {}, {}, 0
+_points_cache = {}
+
+
+def cached_points(name, ranges):
+    """grid_points(ranges), cached per (algorithm, ranges object) so that engines can reuse their launch plans."""
+    key = (name, id(ranges))
+    hit = _points_cache.get(key)
+    if hit is None or hit[0] is not ranges:
+        hit = (ranges, grid_points(ranges))
+        _points_cache[key] = hit
+    return hit[1]
+
+
+def run_engine_device(engine, grids=DEFAULT_GRIDS, u_pad=None):
+    """Enqueue every algorithm's sweep; returns [(name, points, device buffer, plan)] - nothing synchronised."""
+    out = []
     for name, ranges in grids:
-        pts = grid_points(ranges)
-        scores[name] = engine.sweep(name, pts)
+        pts = cached_points(name, ranges)
+        buf, pl = engine.sweep_device(name, pts, u_pad=u_pad)
+        out.append((name, pts, buf, pl))
+    return out
+
+
+def run_engine(engine, grids=DEFAULT_GRIDS):
+    """Device part + one device->host copy per algorithm: {alg: structured scores [U, n_points]} (+ points)."""
+    scores, points, unique = {}, {}, 0
+    for name, pts, buf, pl in run_engine_device(engine, grids):
+        scores[name] = engine.table_to_host(engine.be.view_bytes_as(buf, np.uint8), pl, engine.U)
         points[name] = pts
-        unique += engine.last_unique
+        unique += pl["unique"]
     return scores, points, unique
 
 

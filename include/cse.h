@@ -153,6 +153,13 @@ int cse_stoi_items(const void* tables, const void* wav, int item0, int n_items, 
                    int length, int sr, const void* clean, const void* cache, int finalize,
                    cse_score_t* scores, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Nominal score table from the unique candidates' records: out[u][p] = unique[base[p] + u*stride[p]]
+ * (all [dev]; base / stride are int32 [n_points]).  Grid points that differ only in parameters the
+ * reference ignores (noise_percentile under min_tracking, noise_mu under percentile) are computed
+ * once and receive the identical record here, before the host-side selection scan. */
+int cse_expand_scores(const cse_score_t* unique_scores, const int* base, const int* stride,
+                      int n_utts, int n_points, cse_score_t* out, void* stream);
+
 /* Host-side probe used by the tests: evaluates the special-function fits the gain kernels
  * inline (which = 0: exp(-v/2)[(1+v)I0(v/2)+vI1(v/2)] of Code/mmse.py:92-96; 1: E1(v) of
  * Code/advanced_mmse.py:103) at x[0..n) in the library's precision. */

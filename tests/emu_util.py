@@ -124,6 +124,9 @@ class NumpyBackend:
     def ptr(self, buf):
         return ptr(buf)
 
+    def ptr_at(self, buf, byte_offset):
+        return ctypes.c_void_p(buf.ctypes.data + int(byte_offset))
+
     def stream(self):
         return None
 
