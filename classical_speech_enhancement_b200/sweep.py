@@ -84,3 +84,29 @@ def sweep_dataset(clean, noisy, grids=DEFAULT_GRIDS, sr=16000, select=True, chun
     nominal = sum(len(p) for p in points.values()) * eng.U
     return {"scores": scores, "points": points, "nominal": nominal, "unique": unique * eng.U,
             "selection": select_all(scores, points) if select else None, "engine": eng}
+
+
+def sweep_pairs(pairs, grids=DEFAULT_GRIDS, sr=16000, select=True, chunk_items=4736, engine_kwargs=None):
+    """Variable-length form of :func:`sweep_dataset`: ``pairs`` is a list of (clean, noisy) 1-D arrays
+    (each pair equal length, pair-aligned, 16 kHz).  Pairs are bucketed by length - one engine (and
+    one set of cached spectrograms) per distinct length - and results are returned in input order."""
+    by_len = {}
+    for i, (c, n) in enumerate(pairs):
+        c = np.asarray(c)
+        n = np.asarray(n)
+        if c.ndim != 1 or c.shape != n.shape:
+            raise ValueError(f"pair {i}: clean and noisy must be 1-D arrays of equal length")
+        by_len.setdefault(len(c), []).append(i)
+    scores, points, nominal, unique = None, None, 0, 0
+    for L, idx in sorted(by_len.items()):
+        out = sweep_dataset(np.stack([pairs[i][0] for i in idx]), np.stack([pairs[i][1] for i in idx]), grids=grids,
+                            sr=sr, select=False, chunk_items=chunk_items, engine_kwargs=engine_kwargs)
+        if scores is None:
+            points = out["points"]
+            scores = {name: np.zeros((len(pairs), sc.shape[1]), dtype=sc.dtype) for name, sc in out["scores"].items()}
+        for name, sc in out["scores"].items():
+            scores[name][idx] = sc
+        nominal += out["nominal"]
+        unique += out["unique"]
+    return {"scores": scores, "points": points, "nominal": nominal, "unique": unique,
+            "selection": select_all(scores, points) if select else None}

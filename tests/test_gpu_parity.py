@@ -212,3 +212,44 @@ def test_drop_in_entry_points_on_device():
     res = optimize_parameters(c, n, 16000, wiener_filter, ranges, pesq_scorer=lambda a, b, sr: 2.0, verbose=False)
     _, _, best = oracle.sweep_one_pair(c, n, 16000, oracle.wiener_filter, ranges, pesq_fn=lambda a, b, sr: 2.0)
     assert res["stoi"]["params"] == best["stoi"]["params"]
+
+
+@pytest.mark.parametrize("n_fft,hop", [(256, 64), (256, 128), (2048, 256), (2048, 1024), (1024, 512), (512, 100)])
+def test_wider_operating_range(n_fft, hop):
+    """n_fft 256-2048 (north_star) and hops up to n_fft/2, including a non-power-of-two hop."""
+    c, n = make_pair(13, 40000)
+    c, n = f32(c), f32(n)
+    eng = engine_for(c, n)
+    for alg, extra in (("wiener", dict(alpha=0.95, gain_floor=0.05)),
+                       ("omlsa", dict(alpha=0.9, ksi_min=0.01, gain_floor=0.1, noise_mu=0.95, q=0.4))):
+        p = dict(extra, n_fft=n_fft, hop_length=hop, noise_percentile=20.0, noise_method="min_tracking")
+        wav = eng.enhance(alg, [p])[0, 0]
+        ref = oracle.ALGORITHMS[alg](n, 16000, **p)
+        assert np.abs(wav - ref).max() / np.abs(ref).max() < TOL_WAVE, (alg, n_fft, hop)
+        sc = eng.sweep(alg, [p])[0, 0]
+        rs = score_candidate(c, ref, 16000)
+        assert abs(sc["stoi"] - rs["stoi"]) < TOL_STOI and abs(sc["snr"] - rs["snr"]) < TOL_SNR_DB
+
+
+def test_long_utterance_10s():
+    c, n = make_pair(17, 160000)
+    c, n = f32(c), f32(n)
+    eng = engine_for(c, n)
+    p = dict(alpha=0.98, ksi_min=0.001, gain_min=0.05, gain_max=1.0, n_fft=512, hop_length=128,
+             noise_percentile=10.0, noise_method="percentile")
+    sc = eng.sweep("mmse", [p])[0, 0]
+    rs = score_candidate(c, oracle.mmse(n, 16000, **p), 16000)
+    assert abs(sc["stoi"] - rs["stoi"]) < TOL_STOI and abs(sc["snr"] - rs["snr"]) < TOL_SNR_DB
+
+
+def test_variable_length_pairs_and_full_grid_selection():
+    """Bucketed variable-length sweep over the FULL Wiener grid: every score vs the oracle for one pair."""
+    from classical_speech_enhancement_b200.sweep import sweep_pairs
+    pairs = [tuple(f32(x) for x in make_pair(50, 32000)), tuple(f32(x) for x in make_pair(51, 36000)),
+             tuple(f32(x) for x in make_pair(52, 32000))]
+    out = sweep_pairs(pairs, grids=(("wiener", pr.param_ranges_wiener),))
+    sc = out["scores"]["wiener"]
+    assert sc.shape == (3, 192) and out["nominal"] == 576 and out["unique"] == 432
+    pts, scores, best = oracle.sweep_one_pair(pairs[1][0], pairs[1][1], 16000, oracle.wiener_filter, pr.param_ranges_wiener)
+    assert np.abs(sc[1]["stoi"] - np.array([s["stoi"] for s in scores])).max() < TOL_STOI
+    assert out["selection"]["wiener"][1]["stoi"]["index"] == best["stoi"]["index"]

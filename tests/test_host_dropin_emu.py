@@ -121,3 +121,26 @@ def test_run_algorithm_on_pair_row_schema(tmp_path):
     assert sorted(p.name for p in tmp_path.iterdir()) == [
         "synth_006_spectralSubtractor_optimized_balanced.wav", "synth_006_spectralSubtractor_optimized_pesq.wav",
         "synth_006_spectralSubtractor_optimized_stoi.wav"]
+
+
+def test_sweep_pairs_buckets_by_length_and_result_files(tmp_path):
+    from classical_speech_enhancement_b200.results_io import write_results
+    from classical_speech_enhancement_b200.speech_enhancement_comparison import run_algorithm_on_pair
+    from classical_speech_enhancement_b200.sweep import sweep_dataset, sweep_pairs
+    from classical_speech_enhancement_b200.wiener_filter import wiener_filter
+    grid = (("wiener", {"alpha": [0.95], "gain_floor": [0.02, 0.1], "n_fft": [256], "hop_length": [128],
+                        "noise_percentile": [10.0], "noise_method": ["percentile", "min_tracking"]}),)
+    pairs = [make_pair(0, 9000), make_pair(1, 10000), make_pair(2, 9000)]
+    out = sweep_pairs(pairs, grids=grid)
+    assert out["scores"]["wiener"].shape == (3, 4) and out["nominal"] == 12
+    single = sweep_dataset(pairs[1][0][None], pairs[1][1][None], grids=grid)
+    assert np.array_equal(out["scores"]["wiener"][1], single["scores"]["wiener"][0])
+    c, n = pairs[0]
+    row = run_algorithm_on_pair("wiener", wiener_filter, grid[0][1], f32(c), f32(n), 16000, None, "synth_000",
+                                pesq_scorer=lambda a, b, sr: 1.5, verbose=False)
+    summary = write_results([row], ["wiener"], str(tmp_path))
+    assert summary["wiener"]["count"] == 1 and abs(summary["wiener"]["pesq_noisy_mean"] - 1.5) < 1e-12
+    lines = (tmp_path / "all_results.csv").read_text().splitlines()
+    assert lines[0].startswith("stem,alg,stoi_noisy") and lines[1].startswith("synth_000,wiener,")
+    import json
+    assert json.loads((tmp_path / "all_results.json").read_text())[0]["best_params_stoi"]["n_fft"] == 256
