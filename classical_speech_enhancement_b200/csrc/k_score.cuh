@@ -473,16 +473,17 @@ __global__ void __launch_bounds__(256, 4) stoi_kernel(ScoreArgs a, const double*
         const real* __restrict__ cl = a.clean + (size_t)u * g.L;
         real pn = R(0);
         int bad = 0;
-        for (int i0 = 0; i0 < g.L; i0 += 4 * NT) {
-            real raw[4], cv[4];
+        constexpr int SB = 8;                      // loads in flight per thread
+        for (int i0 = 0; i0 < g.L; i0 += SB * NT) {
+            real raw[SB], cv[SB];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < SB; ++k) {
                 const int i = i0 + tid + k * NT;
                 raw[k] = i < g.L ? xraw(sig, i, lag, g.L) : R(0);
                 cv[k] = i < g.L ? cl[i] : R(0);
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < SB; ++k) {
                 if (!r_finite(raw[k])) bad = 1;
                 const real d = cv[k] - (fin ? r_clip(raw[k], R(-1), R(1)) : raw[k]);
                 pn = r_fma(d, d, pn);
