@@ -147,10 +147,13 @@ struct EnhanceArgs {
     real eps;
 };
 
+#ifndef CSE_ENH_CAP
+#define CSE_ENH_CAP 256
+#endif
 template <int LOG2N> struct EnhanceCfg {
     static constexpr int NFFT = 1 << LOG2N, M = NFFT / 2;
     static constexpr int NPAIR = M / 2;                      // pair slots s: bins (s, M-s); slot 0 = (DC, Nyquist)
-    static constexpr int NTB = NPAIR < 256 ? NPAIR : 256;    // pair threads
+    static constexpr int NTB = NPAIR < CSE_ENH_CAP ? NPAIR : CSE_ENH_CAP;    // pair threads
     static constexpr int PPT = NPAIR / NTB;                  // pair slots per pair thread
     static constexpr int NT = NTB + 32;                      // + one warp whose lane 0 owns the self-paired bin M/2
     static constexpr int F = (8 * NTB) / M;                  // frames per iteration: F * M/8 butterflies == NTB
@@ -163,7 +166,7 @@ template <int LOG2N> struct EnhanceCfg {
 // so it is formed in registers and written straight into the FFT buffer - no separate split
 // pass, no exchange through shared memory.
 template <int ALG, int LOG2N>
-__global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (LOG2N >= 10 ? 3 : 4)) enhance_kernel(EnhanceArgs a) {
+__global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT > 200 ? 3 : 4)) enhance_kernel(EnhanceArgs a) {
     typedef EnhanceCfg<LOG2N> C;
     constexpr int NFFT = C::NFFT, M = C::M, LOG2M = LOG2N - 1, NTB = C::NTB, PPT = C::PPT, NT = C::NT, F = C::F;
     constexpr int XST = C::XST;
