@@ -8,6 +8,7 @@
 #include "k_enhance.cuh"
 #include "k_noise.cuh"
 #include "k_score.cuh"
+#include "k_stoi_stream.cuh"
 
 #include <mutex>
 #include <cstdarg>

@@ -75,10 +75,13 @@ extern "C" int cse_noise_mintrack(const void* P, int n_utts, int n_frames, int n
 
 // ------------------------------------------------------------------ K5 scoring
 static size_t align_smem() { return (size_t)(CSE_FFT_STRIDE(CSE_CORR_P) + FftTwLayout<CSE_CORR_LOG2P, false>::SIZE + 2) * sizeof(real2) + 48 * sizeof(double); }
-static size_t stoi_smem(const ScoreGeom& g) {
-    return 40 * sizeof(double) + sizeof(real) * ((size_t)CSE_STOI_T * CSE_FFT_STRIDE(256) * 2 +
-                                                 (size_t)CSE_STOI_T * (CSE_STOI_K1 - CSE_STOI_K0) +
-                                                 (size_t)2 * CSE_NBANDS * (g.nfrm + 1) + 256 + 320) + sizeof(int) * (size_t)(g.nfr + 2);
+static size_t stoi_smem(const ScoreGeom& g) {      // clean_stoi_kernel
+    return sizeof(real) * ((size_t)CSE_STOI_T * CSE_FFT_STRIDE(256) * 2 + (size_t)CSE_STOI_T * (CSE_STOI_K1 - CSE_STOI_K0) +
+                           (size_t)CSE_NBANDS * (g.nfrm + 1) + 4 + 256 + 320) + sizeof(int) * (size_t)(g.nfr + 2);
+}
+static size_t stoi_stream_smem() {
+    return 40 * sizeof(double) + sizeof(real) * ((size_t)CSE_STOI_T * CSE_FFT_STRIDE(256) * 2 + 5 * CSE_RS_A2 +
+                                                 (size_t)CSE_STOI_RB * 128 + 256 + 320);
 }
 static size_t up64(size_t x) { return (x + 63) & ~(size_t)63; }
 static int check_sr(int sr) {
@@ -113,7 +116,7 @@ extern "C" int cse_prepare_clean(const void* tables, const void* clean, int n_ut
     CSE_LAUNCH(ka, n_utts, 512, align_smem(), stream, a);
     const size_t vsm = (size_t)(8 * (CSE_RS_A + 17) + 40) * sizeof(double);
     CSE_LAUNCH(clean_vad_kernel, n_utts, 256, vsm, stream, a, y10d, energies);
-    auto ks = stoi_kernel<1>;
+    auto ks = clean_stoi_kernel;
     cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stoi_smem(a.g));
     CSE_LAUNCH(ks, n_utts, 256, stoi_smem(a.g), stream, a, (const double*)y10d);
     return check_launch("prepare_clean");
@@ -146,9 +149,9 @@ static int score_items(const void* tables, const void* wav, int item0, int n_ite
         CSE_LAUNCH(ka, n_items, 512, align_smem(), stream, a);
     }
     if (which & 2) {
-        auto ks = stoi_kernel<0>;
-        cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stoi_smem(a.g));
-        CSE_LAUNCH(ks, n_items, 256, stoi_smem(a.g), stream, a, (const double*)nullptr);
+        auto ks = stoi_stream_kernel;
+        cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stoi_stream_smem());
+        CSE_LAUNCH(ks, n_items, 256, stoi_stream_smem(), stream, a);
     }
     return check_launch("score");
 }

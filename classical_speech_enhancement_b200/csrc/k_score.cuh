@@ -61,7 +61,7 @@ struct CleanHeader {
 
 struct ScoreGeom {
     int L, Nc, maxlag, nblocks, npairs, n10, nfr, nfrm, jmax;
-    size_t off_kept, off_need, off_xtob, off_seg, off_rsum, off_q, bytes;
+    size_t off_kept, off_need, off_hbmap, off_xtob, off_seg, off_rsum, off_q, bytes;
 };
 
 static inline ScoreGeom score_geom(int L) {
@@ -79,6 +79,7 @@ static inline ScoreGeom score_geom(int L) {
     size_t o = up(sizeof(CleanHeader));
     g.off_kept = o; o = up(o + sizeof(int) * (size_t)(g.nfr + 1));
     g.off_need = o; o = up(o + (size_t)((g.n10 + 4) / 5 + 8));       // one byte per resampler group of 5 outputs
+    g.off_hbmap = o; o = up(o + sizeof(int) * (size_t)3 * (g.nfr + 2));   // per 128-sample hop-block: (jA, jB, #kept below)
     g.off_xtob = o; o = up(o + sizeof(real) * (size_t)CSE_NBANDS * (g.nfrm + 1));
     g.off_seg = o; o = up(o + sizeof(real) * (size_t)3 * CSE_NBANDS * (g.jmax + 1));
     g.off_rsum = o; o = up(o + sizeof(real) * (size_t)(2 * CSE_MAXLAG + 1));
@@ -314,57 +315,7 @@ CSE_D void resample_pass(const real* __restrict__ sig, int L, int lag, bool fina
     __syncthreads();
 }
 
-// Candidate-path resampler: one pass produces y10[5a + p] for 512 groups a.  Each thread owns TWO
-// groups (al, al + 256) whose input samples sit side by side in a float2 tile, so one LDS.64 feeds
-// both and every tap is ONE packed FFMA2 (tap broadcast from the constant bank through a uniform
-// register): 581 FFMA2 + 123 LDS.64 per two groups instead of 2 x (581 FFMA + 123 LDS).
-#define CSE_RS_A2 512
-CSE_D void resample_pass2(const real* __restrict__ sig, int L, int lag, bool finalize, real2* xs2, int a0,
-                          real* __restrict__ y10, int n10, int tid, int nth, const unsigned char* __restrict__ need) {
-    constexpr int H = CSE_RS_A2 / 2, AP2 = H + 17;
-    const int j0 = 8 * a0 - 64;
-    // tile load: all global loads of the thread are issued before the first shared-memory store
-    constexpr int TOT = 8 * (CSE_RS_A2 + 17), PERT = (TOT + 255) / 256;
-    {
-        real v[PERT];
-#pragma unroll
-        for (int k = 0; k < PERT; ++k) { const int jj = tid + k * nth; v[k] = jj < TOT ? xhat(sig, j0 + jj, lag, L, finalize) : R(0); }
-#pragma unroll
-        for (int k = 0; k < PERT; ++k) {
-            const int jj = tid + k * nth;
-            if (jj < TOT) {
-                const int c = jj & 7, ap = jj >> 3;
-                if (ap < AP2) xs2[c * AP2 + ap].x = v[k];
-                if (ap >= H) xs2[c * AP2 + ap - H].y = v[k];
-            }
-        }
-    }
-    __syncthreads();
-    for (int al = tid; al < H; al += nth) {
-        const int alo = a0 + al, ahi = alo + H;
-        const bool want_lo = 5 * alo < n10 && need[alo], want_hi = 5 * ahi < n10 && need[ahi];
-        if (want_lo || want_hi) {
-            real2 acc[5];
-#pragma unroll
-            for (int p = 0; p < 5; ++p) acc[p] = mk2(R(0), R(0));
-#pragma unroll
-            for (int jj = 6; jj <= 128; ++jj) {                 // rows 0-5 and 129-135 hold no tap
-                const real2 x = xs2[(jj & 7) * AP2 + al + (jj >> 3)];
-#pragma unroll
-                for (int p = 0; p < 5; ++p) {
-                    const int idx = 8 * p + 610 - 5 * jj;        // compile-time after unrolling
-                    if (idx >= 0 && idx <= 580) acc[p] = cfma2(x, mk2(c_rs[jj * 8 + p], c_rs[jj * 8 + p]), acc[p]);
-                }
-            }
-#pragma unroll
-            for (int p = 0; p < 5; ++p) {
-                if (want_lo && 5 * alo + p < n10) y10[5 * alo + p] = acc[p].x;
-                if (want_hi && 5 * ahi + p < n10) y10[5 * ahi + p] = acc[p].y;
-            }
-        }
-    }
-    __syncthreads();
-}
+#define CSE_RS_A2 512                  // candidate-side resampler tile (k_stoi_stream.cuh): groups of 5 outputs per pass
 
 // clean-side resampling + VAD (pystoi remove_silent_frames, mask from the clean signal only)
 // grid U, block 256; y10 (real) goes to the workspace for clean_stoi.
@@ -427,33 +378,43 @@ __global__ void __launch_bounds__(256) clean_vad_kernel(ScoreArgs a, double* __r
             for (int j = 0; j < K && !nd; ++j) { const int f = kept[j]; if (f >= f0 && f <= f1) nd = 1; else if (f > f1) break; }
             need[a5] = nd;
         }
+        // hop-block map for the streaming STOI kernel.  Hop-block hb = y10[128 hb, 128 hb + 128) is the first
+        // half of kept frame hb (index jA in the kept list) and the second half of kept frame hb-1 (which
+        // starts the overlap-added block jB = index(hb-1) + 1); count = kept frames with frame index < hb.
+        int* hbmap = reinterpret_cast<int*>(rec + g.off_hbmap);
+        for (int hb = tid; hb < g.nfr + 2; hb += 256) {
+            int ja = -1, jb = -1, cnt = 0;
+            for (int j = 0; j < K; ++j) {
+                const int f = kept[j];
+                if (f < hb) ++cnt;
+                if (f == hb) ja = j;
+                if (f == hb - 1) jb = j + 1;
+            }
+            hbmap[3 * hb] = ja; hbmap[3 * hb + 1] = jb; hbmap[3 * hb + 2] = cnt;
+        }
     }
 }
 
-// ---------------------------------------------------------------- STOI + SNR
-// MODE 0: score a candidate.  MODE 1: clean-side pass (band envelopes + segment statistics into
-// the cache; y10 already in the workspace as double).
-template <int MODE>
-__global__ void __launch_bounds__(256, 4) stoi_kernel(ScoreArgs a, const double* __restrict__ y10d) {
+// ---------------------------------------------------------------- clean-side STOI caches
+// Band envelopes of the clean signal and, per (segment, band), its norm, mean and 1/(centred norm +
+// EPS) into the per-utterance cache (the candidate side is k_stoi_stream.cuh).  y10d: the clean
+// signal at 10 kHz (double, from clean_vad_kernel).
+__global__ void __launch_bounds__(256, 4) clean_stoi_kernel(ScoreArgs a, const double* __restrict__ y10d) {
     constexpr int T = CSE_STOI_T, BST = CSE_FFT_STRIDE(256), NK = CSE_STOI_K1 - CSE_STOI_K0, NT = 256;
     CSE_DYN_SMEM(smem_raw);
     const ScoreGeom& g = a.g;
-    const int tid = threadIdx.x, li = blockIdx.x, item = a.item0 + li;
-    const int u = MODE == 1 ? item : item / a.per_utt;
+    const int tid = threadIdx.x, u = blockIdx.x;
     unsigned char* rec = a.cache + (size_t)u * g.bytes;
     const CleanHeader* hdr = reinterpret_cast<const CleanHeader*>(rec);
     const int* __restrict__ kept = reinterpret_cast<const int*>(rec + g.off_kept);
     real* xtob_c = reinterpret_cast<real*>(rec + g.off_xtob);
     real* seg_c = reinterpret_cast<real*>(rec + g.off_seg);
-    const unsigned char* __restrict__ need = rec + g.off_need;   // resampler groups that feed a kept frame
     const int K = hdr->K, Kf = K > 0 ? K - 1 : 0, J = hdr->J;
 
-    double* scratch = reinterpret_cast<double*>(smem_raw);                    // 40 doubles
-    real2* fbuf = reinterpret_cast<real2*>(scratch + 40);                     // T * BST (aliases the resampler tile)
+    real2* fbuf = reinterpret_cast<real2*>(smem_raw);                         // T * BST
     real* pw = reinterpret_cast<real*>(fbuf + T * BST);                       // T * NK
     real* ytob = pw + T * NK;                                                 // 15 * Kf
-    real* xtob = ytob + CSE_NBANDS * (g.nfrm + 1);                            // 15 * Kf (MODE 0)
-    real* w_s = xtob + CSE_NBANDS * (g.nfrm + 1);                             // 256: np.hanning(258)[1:-1]
+    real* w_s = ytob + ((CSE_NBANDS * (g.nfrm + 1) + 3) & ~3);                // 256: np.hanning(258)[1:-1] (16-byte aligned)
     real2* tws = reinterpret_cast<real2*>(w_s + 256);                         // per-pass twiddles of the 256-point FFT
     int* kept_s = reinterpret_cast<int*>(tws + 160);                          // nfr + 2 kept-frame indices
 
@@ -461,94 +422,29 @@ __global__ void __launch_bounds__(256, 4) stoi_kernel(ScoreArgs a, const double*
     load_pass_twiddles<8, true>(tws, a.T->tw, tid, NT);
     for (int i = tid; i < K; i += NT) kept_s[i] = kept[i];
     __syncthreads();
-    const real* __restrict__ sig = a.wav + (size_t)li * g.L;
-    real* y10 = a.y10 + (size_t)li * g.n10;
-    int lag = 0, flags = CSE_FLAG_VALID;
-    const bool fin = MODE == 0 && a.finalize;
-    if (MODE == 0) {
-        lag = a.lagflags[2 * li];
-        flags = a.lagflags[2 * li + 1];
-        // global SNR: 10 log10( sum c^2 / (sum (c - x)^2 + 1e-10) ), and the finite check of
-        // finalize_enhanced over the samples that survive the shift (:102-103)
-        const real* __restrict__ cl = a.clean + (size_t)u * g.L;
-        real pn = R(0);
-        int bad = 0;
-        constexpr int SB = 8;                      // loads in flight per thread
-        for (int i0 = 0; i0 < g.L; i0 += SB * NT) {
-            real raw[SB], cv[SB];
-#pragma unroll
-            for (int k = 0; k < SB; ++k) {
-                const int i = i0 + tid + k * NT;
-                raw[k] = i < g.L ? xraw(sig, i, lag, g.L) : R(0);
-                cv[k] = i < g.L ? cl[i] : R(0);
-            }
-#pragma unroll
-            for (int k = 0; k < SB; ++k) {
-                if (!r_finite(raw[k])) bad = 1;
-                const real d = cv[k] - (fin ? r_clip(raw[k], R(-1), R(1)) : raw[k]);
-                pn = r_fma(d, d, pn);
-            }
-        }
-        const double nbad = block_sum<double>((double)bad, scratch);
-        if (nbad > 0.0) {
-            if (tid == 0) { cse_score_t sc; sc.stoi = R(0); sc.snr = R(0); sc.lag = lag; sc.flags = 0; a.scores[item] = sc; }
-            return;
-        }
-        const double pnoise = block_sum<double>((double)pn, scratch);
-        for (int i = tid; i < CSE_NBANDS * Kf; i += NT) xtob[i] = xtob_c[i];
-        __syncthreads();
-        const int na = (g.n10 + 4) / 5;
-        for (int a0 = 0; a0 < na; a0 += CSE_RS_A2)
-            resample_pass2(sig, g.L, lag, fin, reinterpret_cast<real2*>(fbuf), a0, y10, g.n10, tid, NT, need);
-        __threadfence_block();
-        __syncthreads();
-        if (tid == 0) {
-            real snr;
-            if (pnoise == 0.0) { snr = cse_inf(); flags |= CSE_FLAG_SNR_INF; }
-            else snr = (real)(10.0 * log10(hdr->energy / (pnoise + 1e-10)));
-            a.scores[item].snr = snr;
-            a.scores[item].lag = lag;
-        }
-    }
-    if (Kf < CSE_NSEG) {
-        if (MODE == 0 && tid == 0) { a.scores[item].stoi = R(1e-5); a.scores[item].flags = flags | CSE_FLAG_STOI_SHORT; }
-        return;
-    }
+    if (Kf < CSE_NSEG) return;
     const int* __restrict__ edges = a.T->stoi_edges;
-    const double* ydu = MODE == 1 ? y10d + (size_t)u * g.n10 : nullptr;
-    auto ysamp = [&](int i) -> real { return MODE == 1 ? (real)ydu[i] : y10[i]; };
+    const double* ydu = y10d + (size_t)u * g.n10;
 
     for (int m0 = 0; m0 < Kf; m0 += T) {
-        // frames of the silence-removed signal: sample n of frame m is
-        //   w[n] * (F_m[n] + F_{m-1}[n+128])  (n < 128),  w[n] * (F_{m+1}[n-128] + F_m[n])  (n >= 128),
-        // F_j[n] = w[n] * y10[128 kept[j] + n]
         // frame m = w .* (B_m ++ B_{m+1}), B_j[n] = w[n] y10[128 kept[j] + n] + w[128+n] y10[128 kept[j-1] + 128 + n]
-        // (the overlap-added blocks of the silence-removed signal).  4 packed samples per thread, all
-        // y10 loads issued first.
-        {
-            constexpr int PER = T * 128 / NT;
-            real ya[PER][2], yb[PER][2];
-#pragma unroll
-            for (int k = 0; k < PER; ++k) {
-                const int idx = tid + k * NT, f = idx >> 7, mm = idx & 127, m = m0 + f;
-                const int j = mm < 64 ? m : m + 1, nn = (2 * mm) & 127;
-                const bool on = m < Kf;
-                const int k1 = on ? 128 * kept_s[j] + nn : 0;
-                const int k0 = (on && j > 0) ? 128 * kept_s[j - 1] + 128 + nn : -1;
-                ya[k][0] = on ? ysamp(k1) : R(0);
-                ya[k][1] = on ? ysamp(k1 + 1) : R(0);
-                yb[k][0] = k0 >= 0 ? ysamp(k0) : R(0);
-                yb[k][1] = k0 >= 0 ? ysamp(k0 + 1) : R(0);
+        // (the overlap-added blocks of the silence-removed signal)
+        for (int idx = tid; idx < T * 128; idx += NT) {
+            const int f = idx >> 7, mm = idx & 127, m = m0 + f;
+            const int j = mm < 64 ? m : m + 1, nn = (2 * mm) & 127, n = 2 * mm;
+            real2 v = mk2(R(0), R(0));
+            if (m < Kf) {
+                const int k1 = 128 * kept_s[j] + nn;
+                real b0 = w_s[nn] * (real)ydu[k1], b1 = w_s[nn + 1] * (real)ydu[k1 + 1];
+                if (j > 0) {
+                    const int k0 = 128 * kept_s[j - 1] + 128 + nn;
+                    b0 = r_fma(w_s[nn + 128], (real)ydu[k0], b0);
+                    b1 = r_fma(w_s[nn + 129], (real)ydu[k0 + 1], b1);
+                }
+                v = mk2(w_s[n] * b0, w_s[n + 1] * b1);
             }
-#pragma unroll
-            for (int k = 0; k < PER; ++k) {
-                const int idx = tid + k * NT, f = idx >> 7, mm = idx & 127;
-                const int nn = (2 * mm) & 127, n = 2 * mm;
-                const real b0 = r_fma(w_s[nn], ya[k][0], w_s[nn + 128] * yb[k][0]);
-                const real b1 = r_fma(w_s[nn + 1], ya[k][1], w_s[nn + 129] * yb[k][1]);
-                fbuf[f * BST + SIDX(mm)] = mk2(w_s[n] * b0, w_s[n + 1] * b1);
-                fbuf[f * BST + SIDX(mm + 128)] = mk2(R(0), R(0));
-            }
+            fbuf[f * BST + SIDX(mm)] = v;
+            fbuf[f * BST + SIDX(mm + 128)] = mk2(R(0), R(0));
         }
         __syncthreads();
         fft_dif<8, false, 0>(fbuf, T, BST, tws, tid, NT);
@@ -572,51 +468,18 @@ __global__ void __launch_bounds__(256, 4) stoi_kernel(ScoreArgs a, const double*
         }
         __syncthreads();
     }
-
     const real EPS = R(2.220446049250313e-16);
-    if (MODE == 1) {
-        // clean side: envelopes + per (segment, band) norm, mean, 1/(centred norm + EPS)
-        for (int i = tid; i < CSE_NBANDS * Kf; i += NT) xtob_c[i] = ytob[i];
-        for (int idx = tid; idx < J * CSE_NBANDS; idx += NT) {
-            const int b = idx / J, j = idx - b * J;        // segment index fastest: a warp reads consecutive envelopes
-            const real* x = ytob + b * Kf + j;
-            real s1 = R(0), s2 = R(0);
-            for (int n = 0; n < CSE_NSEG; ++n) { s1 += x[n]; s2 = r_fma(x[n], x[n], s2); }
-            const real mean = s1 / R(CSE_NSEG);
-            real c2 = R(0);
-            for (int n = 0; n < CSE_NSEG; ++n) { const real d = x[n] - mean; c2 = r_fma(d, d, c2); }
-            seg_c[(size_t)0 * J * CSE_NBANDS + idx] = r_sqrt(s2);
-            seg_c[(size_t)1 * J * CSE_NBANDS + idx] = mean;
-            seg_c[(size_t)2 * J * CSE_NBANDS + idx] = R(1) / (r_sqrt(c2) + EPS);
-        }
-        return;
-    }
-    // d = mean over (segment, band) of corr( clip(alpha Y, (1 + 10^(15/20)) X) , X )
-    const real clipc = R(1) + R(5.623413251903491);
-    real dsum = R(0);
+    for (int i = tid; i < CSE_NBANDS * Kf; i += NT) xtob_c[i] = ytob[i];
     for (int idx = tid; idx < J * CSE_NBANDS; idx += NT) {
-        const int b = idx / J, j = idx - b * J;            // (band, segment), segment fastest: conflict-free, coalesced
-        const real* x = xtob + b * Kf + j;
-        const real* y = ytob + b * Kf + j;
-        const real xn = seg_c[idx], xmean = seg_c[(size_t)J * CSE_NBANDS + idx], xinv = seg_c[(size_t)2 * J * CSE_NBANDS + idx];
-        real y2 = R(0);
-        for (int n = 0; n < CSE_NSEG; ++n) y2 = r_fma(y[n], y[n], y2);
-        const real alpha = xn / (r_sqrt(y2) + EPS);
-        real s1 = R(0);
-        for (int n = 0; n < CSE_NSEG; ++n) s1 += r_min(alpha * y[n], clipc * x[n]);
-        const real ymean = s1 / R(CSE_NSEG);
-        real c2 = R(0), cx = R(0);
-        for (int n = 0; n < CSE_NSEG; ++n) {
-            const real d = r_min(alpha * y[n], clipc * x[n]) - ymean;
-            c2 = r_fma(d, d, c2);
-            cx = r_fma(d, x[n] - xmean, cx);
-        }
-        dsum += cx * xinv / (r_sqrt(c2) + EPS);
-    }
-    const double dtot = block_sum<double>((double)dsum, scratch);
-    if (tid == 0) {
-        a.scores[item].stoi = (real)(dtot / ((double)J * CSE_NBANDS));
-        a.scores[item].flags = flags;
+        const int b = idx / J, j = idx - b * J;        // (band, segment), segment fastest
+        const real* x = ytob + b * Kf + j;
+        real s1 = R(0), s2 = R(0);
+        for (int n = 0; n < CSE_NSEG; ++n) { s1 += x[n]; s2 = r_fma(x[n], x[n], s2); }
+        const real mean = s1 / R(CSE_NSEG);
+        real c2 = R(0);
+        for (int n = 0; n < CSE_NSEG; ++n) { const real d = x[n] - mean; c2 = r_fma(d, d, c2); }
+        seg_c[(size_t)0 * J * CSE_NBANDS + idx] = r_sqrt(s2);
+        seg_c[(size_t)1 * J * CSE_NBANDS + idx] = mean;
+        seg_c[(size_t)2 * J * CSE_NBANDS + idx] = R(1) / (r_sqrt(c2) + EPS);
     }
 }
-

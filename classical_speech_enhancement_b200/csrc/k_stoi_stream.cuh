@@ -1,0 +1,247 @@
+// K5b (candidate side): SNR + STOI in ONE streaming pass over the candidate waveform.
+//
+// Restates calculate_snr (Code/evaluation_metrics.py:39-58) and pystoi.stoi(extended=False)
+// (Code/evaluation_metrics.py:30-36) for one finalized candidate, as k_score.cuh describes, but
+// without the global 10 kHz scratch signal of the first version (profiles/r01f: 491 KB of DRAM
+// traffic per candidate against 192 KB algorithmic).  The waveform is read exactly once:
+//
+//   for each tile of 4096 input samples (2560 output samples = 20 hop-blocks of 128):
+//     1. load the tile (+ filter margins) de-interleaved into shared memory; the same loads feed the
+//        SNR sums and the finite check of finalize_enhanced;
+//     2. polyphase-resample it into a shared-memory tile (packed two-group FFMA2 form);
+//     3. fold the needed hop-blocks into the overlap-added blocks of the silence-removed signal,
+//          B_j[n] = w[n] y10[128 kept[j] + n] + w[128+n] y10[128 kept[j-1] + 128 + n],
+//        kept in a ring of 32 blocks (hop-block -> (j, j') map and running kept count cached per
+//        utterance by the clean-side pass);
+//     4. as soon as 9 consecutive blocks are complete, transform 8 frames  w .* (B_m ++ B_{m+1})
+//        (batched 256-point complex DIF FFTs), take third-octave band envelopes.
+//   then the 30-frame segment correlation against the cached clean statistics.
+// Only the 15 x K band envelopes (14 KB) go through a global scratch row (they are re-read into
+// shared memory for the correlation when they fit).
+#pragma once
+#include "k_score.cuh"
+
+#define CSE_STOI_RB 32                 // ring of overlap-added blocks
+#define CSE_STOI_HBT (5 * CSE_RS_A2 / 128)   // hop-blocks produced per resampler tile (20)
+
+__global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
+    constexpr int T = CSE_STOI_T, BST = CSE_FFT_STRIDE(256), NK = CSE_STOI_K1 - CSE_STOI_K0, NT = 256;
+    constexpr int H = CSE_RS_A2 / 2, AP2 = H + 17, RB = CSE_STOI_RB, HBT = CSE_STOI_HBT, YT = 5 * CSE_RS_A2;
+    CSE_DYN_SMEM(smem_raw);
+    const ScoreGeom& g = a.g;
+    const int tid = threadIdx.x, li = blockIdx.x, item = a.item0 + li;
+    const int u = item / a.per_utt;
+    const unsigned char* rec = a.cache + (size_t)u * g.bytes;
+    const CleanHeader* hdr = reinterpret_cast<const CleanHeader*>(rec);
+    const int* __restrict__ kept = reinterpret_cast<const int*>(rec + g.off_kept);
+    const int* __restrict__ hbmap = reinterpret_cast<const int*>(rec + g.off_hbmap);   // [nfr + 2][3]: jA, jB, count
+    const real* __restrict__ xtob = reinterpret_cast<const real*>(rec + g.off_xtob);
+    const real* __restrict__ seg_c = reinterpret_cast<const real*>(rec + g.off_seg);
+    const unsigned char* __restrict__ need = rec + g.off_need;
+    const int K = hdr->K, Kf = K > 0 ? K - 1 : 0, J = hdr->J;
+    const int nhb = g.nfr + 1;
+
+    double* scratch = reinterpret_cast<double*>(smem_raw);                    // 40 doubles
+    real2* fbuf = reinterpret_cast<real2*>(scratch + 40);                     // T * BST; input tile during resampling
+    real* yt = reinterpret_cast<real*>(fbuf + T * BST);                       // YT resampled samples; band powers during FFT batches
+    real* ring = yt + YT;                                                     // RB * 128
+    real* w_s = ring + RB * 128;                                              // 256
+    real2* tws = reinterpret_cast<real2*>(w_s + 256);                         // 160
+    real2* xs2 = fbuf;
+    real* pw = yt;
+
+    for (int i = tid; i < 256; i += NT) w_s[i] = a.T->stoi_win[i];
+    load_pass_twiddles<8, true>(tws, a.T->tw, tid, NT);
+    const real* __restrict__ sig = a.wav + (size_t)li * g.L;
+    const real* __restrict__ cl = a.clean + (size_t)u * g.L;
+    real* ytob_g = a.y10 + (size_t)li * g.n10;          // scratch row: 15 * Kf band envelopes (n10 >= 15 Kf)
+    const int lag = a.lagflags[2 * li];
+    int flags = a.lagflags[2 * li + 1];
+    const bool fin = a.finalize != 0;
+    const int L = g.L, n10 = g.n10;
+    const bool do_stoi = Kf >= CSE_NSEG;
+    __syncthreads();
+
+    real pn = R(0);
+    int bad = 0, m_next = 0;
+    const int na = (n10 + 4) / 5;
+    const int* __restrict__ edges = a.T->stoi_edges;
+    for (int a0 = 0, t = 0; a0 < na; a0 += CSE_RS_A2, ++t) {
+        // ---- 1. input tile, SNR sums and finite check on the samples this tile owns
+        {
+            constexpr int TOT = 8 * (CSE_RS_A2 + 17), PERT = (TOT + NT - 1) / NT;
+            const int j0 = 8 * a0 - 64;
+            real raw[PERT], cv[PERT];
+#pragma unroll
+            for (int k = 0; k < PERT; ++k) {
+                const int jj = tid + k * NT, j = j0 + jj;
+                const bool own = jj >= 64 && jj < 64 + 8 * CSE_RS_A2 && j < L;        // each sample owned by one tile
+                raw[k] = jj < TOT ? xraw(sig, j, lag, L) : R(0);
+                cv[k] = own ? cl[j] : R(0);
+            }
+#pragma unroll
+            for (int k = 0; k < PERT; ++k) {
+                const int jj = tid + k * NT, j = j0 + jj;
+                if (jj < TOT) {
+                    const real v = fin ? r_clip(raw[k], R(-1), R(1)) : raw[k];
+                    if (jj >= 64 && jj < 64 + 8 * CSE_RS_A2 && j < L) {
+                        if (!r_finite(raw[k])) bad = 1;
+                        const real d = cv[k] - v;
+                        pn = r_fma(d, d, pn);
+                    }
+                    const int c = jj & 7, ap = jj >> 3;
+                    if (ap < AP2) xs2[c * AP2 + ap].x = v;
+                    if (ap >= H) xs2[c * AP2 + ap - H].y = v;
+                }
+            }
+        }
+        __syncthreads();
+        if (!do_stoi) continue;                                                   // uniform: SNR only (the next tile load
+                                                                                  // only overwrites what nobody reads)
+        // ---- 2. resample into the shared tile: yt[5 (a - a0) + p]
+        for (int al = tid; al < H; al += NT) {
+            const int alo = a0 + al, ahi = alo + H;
+            const bool want_lo = 5 * alo < n10 && need[alo], want_hi = 5 * ahi < n10 && need[ahi];
+            if (want_lo || want_hi) {
+                real2 acc[5];
+#pragma unroll
+                for (int p = 0; p < 5; ++p) acc[p] = mk2(R(0), R(0));
+#pragma unroll
+                for (int jj = 6; jj <= 128; ++jj) {
+                    const real2 x = xs2[(jj & 7) * AP2 + al + (jj >> 3)];
+#pragma unroll
+                    for (int p = 0; p < 5; ++p) {
+                        const int idx = 8 * p + 610 - 5 * jj;
+                        if (idx >= 0 && idx <= 580) acc[p] = cfma2(x, mk2(c_rs[jj * 8 + p], c_rs[jj * 8 + p]), acc[p]);
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < 5; ++p) { yt[5 * al + p] = acc[p].x; yt[5 * (al + H) + p] = acc[p].y; }
+            }
+        }
+        __syncthreads();
+        // ---- 3. fold the tile's hop-blocks into the overlap-added blocks B_j.  A block's first
+        // contribution (the second half of kept frame j-1) ASSIGNS, the other one ADDS; when both come
+        // from one hop-block they are written together, otherwise the add runs after a barrier.
+        for (int e = tid; e < YT; e += NT) {
+            const int hb = HBT * t + (e >> 7), n = e & 127;
+            if (hb < nhb) {
+                const int ja = hbmap[3 * hb], jb = hbmap[3 * hb + 1];
+                if (jb >= 0 && jb < K) {
+                    const real y = yt[e];
+                    real v = w_s[128 + n] * y;
+                    if (ja == jb) v = r_fma(w_s[n], y, v);    // consecutive kept frames share the hop-block
+                    ring[(jb & (RB - 1)) * 128 + n] = v;
+                }
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < YT; e += NT) {
+            const int hb = HBT * t + (e >> 7), n = e & 127;
+            if (hb < nhb) {
+                const int ja = hbmap[3 * hb], jb = hbmap[3 * hb + 1];
+                if (ja >= 0 && ja != jb) {                    // first half of kept frame ja completes block ja
+                    const int slot = (ja & (RB - 1)) * 128 + n;
+                    ring[slot] = r_fma(w_s[n], yt[e], ja > 0 ? ring[slot] : R(0));
+                }
+            }
+        }
+        __syncthreads();
+        // ---- 4. transform every batch of T frames whose blocks are complete
+        const int hb_end = HBT * (t + 1) < nhb ? HBT * (t + 1) : nhb;
+        const int jdone = hbmap[3 * hb_end + 2];              // kept frames with index < hb_end -> blocks B_0..B_{jdone-1} complete
+        const bool last = a0 + CSE_RS_A2 >= na;
+        while (m_next < Kf && (m_next + T <= jdone - 1 || last)) {
+            const int m0 = m_next;
+            for (int idx = tid; idx < T * 128; idx += NT) {
+                const int f = idx >> 7, mm = idx & 127, m = m0 + f;
+                const int j = mm < 64 ? m : m + 1, nn = (2 * mm) & 127, n = 2 * mm;
+                real2 v = mk2(R(0), R(0));
+                if (m < Kf) {
+                    const real* B = ring + (j & (RB - 1)) * 128;
+                    v = mk2(w_s[n] * B[nn], w_s[n + 1] * B[nn + 1]);
+                }
+                fbuf[f * BST + SIDX(mm)] = v;
+                fbuf[f * BST + SIDX(mm + 128)] = mk2(R(0), R(0));
+            }
+            __syncthreads();
+            fft_dif<8, false, 0>(fbuf, T, BST, tws, tid, NT);
+            for (int idx = tid; idx < T * NK; idx += NT) {
+                const int f = idx / NK, k = CSE_STOI_K0 + (idx - f * NK);
+                const real2* zf = fbuf + f * BST;
+                const real2 z0 = zf[SIDX(brev_n(k, 8))], z1 = zf[SIDX(brev_n(256 - k, 8))];
+                const real2 E = mk2(R(0.5) * (z0.x + z1.x), R(0.5) * (z0.y - z1.y));
+                const real2 O = mk2(R(0.5) * (z0.y + z1.y), R(-0.5) * (z0.x - z1.x));
+                const real2 X = cadd(E, cmul(O, tw_load(a.T->tw, k * (CSE_TW_N / 512))));
+                pw[idx] = X.x * X.x + X.y * X.y;
+            }
+            __syncthreads();
+            for (int idx = tid; idx < T * CSE_NBANDS; idx += NT) {
+                const int f = idx / CSE_NBANDS, b = idx - f * CSE_NBANDS, m = m0 + f;
+                if (m < Kf) {
+                    real sacc = R(0);
+                    for (int k = edges[b]; k < edges[b + 1]; ++k) sacc += pw[f * NK + k - CSE_STOI_K0];
+                    ytob_g[b * Kf + m] = r_sqrt(sacc);
+                }
+            }
+            __syncthreads();
+            m_next += T;
+        }
+    }
+
+    // ---- SNR, validity
+    const double nbad = block_sum<double>((double)bad, scratch);
+    const double pnoise = block_sum<double>((double)pn, scratch);
+    if (nbad > 0.0) {
+        if (tid == 0) { cse_score_t sc; sc.stoi = R(0); sc.snr = R(0); sc.lag = lag; sc.flags = 0; a.scores[item] = sc; }
+        return;
+    }
+    if (tid == 0) {
+        real snr;
+        if (pnoise == 0.0) { snr = cse_inf(); flags |= CSE_FLAG_SNR_INF; }
+        else snr = (real)(10.0 * log10(hdr->energy / (pnoise + 1e-10)));
+        a.scores[item].snr = snr;
+        a.scores[item].lag = lag;
+    }
+    if (!do_stoi) {
+        if (tid == 0) { a.scores[item].stoi = R(1e-5); a.scores[item].flags = flags | CSE_FLAG_STOI_SHORT; }
+        return;
+    }
+    // ---- segment correlation; envelopes come back into shared memory when they fit
+    __threadfence_block();
+    __syncthreads();
+    real* ysm = reinterpret_cast<real*>(fbuf);
+    const bool fits = CSE_NBANDS * Kf <= 2 * T * BST + YT + RB * 128;      // fbuf + yt + ring are free now
+    if (fits) {
+        for (int i = tid; i < CSE_NBANDS * Kf; i += NT) ysm[i] = ytob_g[i];
+        __syncthreads();
+    }
+    const real* ytob = fits ? ysm : ytob_g;
+    const real EPS = R(2.220446049250313e-16);
+    const real clipc = R(1) + R(5.623413251903491);
+    real dsum = R(0);
+    for (int idx = tid; idx < J * CSE_NBANDS; idx += NT) {
+        const int b = idx / J, j = idx - b * J;
+        const real* x = xtob + b * Kf + j;
+        const real* y = ytob + b * Kf + j;
+        const real xn = seg_c[idx], xmean = seg_c[(size_t)J * CSE_NBANDS + idx], xinv = seg_c[(size_t)2 * J * CSE_NBANDS + idx];
+        real y2 = R(0);
+        for (int n = 0; n < CSE_NSEG; ++n) y2 = r_fma(y[n], y[n], y2);
+        const real alpha = xn / (r_sqrt(y2) + EPS);
+        real s1 = R(0);
+        for (int n = 0; n < CSE_NSEG; ++n) s1 += r_min(alpha * y[n], clipc * x[n]);
+        const real ymean = s1 / R(CSE_NSEG);
+        real c2 = R(0), cx = R(0);
+        for (int n = 0; n < CSE_NSEG; ++n) {
+            const real d = r_min(alpha * y[n], clipc * x[n]) - ymean;
+            c2 = r_fma(d, d, c2);
+            cx = r_fma(d, x[n] - xmean, cx);
+        }
+        dsum += cx * xinv / (r_sqrt(c2) + EPS);
+    }
+    const double dtot = block_sum<double>((double)dsum, scratch);
+    if (tid == 0) {
+        a.scores[item].stoi = (real)(dtot / ((double)J * CSE_NBANDS));
+        a.scores[item].flags = flags;
+    }
+}
