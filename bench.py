@@ -331,7 +331,8 @@ def main():
         by = items * per
         f = fam.setdefault(kind, [0.0, 0.0, 0])
         f[0] += by; f[1] += ms; f[2] += items
-        kname = (f"enhance_kernel<{alg}, {n_fft.bit_length() - 1}>" if kind == "enhance" else f"{kind}_kernel<0>")
+        kname = (f"enhance_kernel<{alg}, {n_fft.bit_length() - 1}>" if kind == "enhance"
+                 else ("stoi_stream_kernel" if kind == "stoi" else "align_kernel<0>"))
         t = tags.setdefault(kname, [0.0, 0.0, 0, per])
         t[0] += by; t[1] += ms; t[2] += items
     peaks, traffic_tab = {}, {}
