@@ -126,7 +126,7 @@ extern "C" size_t cse_score_workspace_bytes(int n_items, int length, int sr) {
     (void)sr;
     if (length <= 0 || n_items <= 0) return 0;
     const ScoreGeom g = score_geom(length);
-    return up64((size_t)n_items * g.n10 * sizeof(real)) + up64((size_t)n_items * 2 * sizeof(int));
+    return up64((size_t)n_items * score_row_reals(g.nfrm) * sizeof(real)) + up64((size_t)n_items * 2 * sizeof(int));
 }
 
 // scores items [item0, item0 + n_items); wav holds only those items.  which: 1 = alignment kernel,
@@ -142,7 +142,7 @@ static int score_items(const void* tables, const void* wav, int item0, int n_ite
     a.g = score_geom(length);
     if (stoi_smem(a.g) > CSE_MAX_SMEM) return fail(CSE_EUNSUPPORTED, "utterance too long for the STOI kernel's shared memory (%d samples)", length);
     a.y10 = (real*)workspace;
-    a.lagflags = (int*)((unsigned char*)workspace + up64((size_t)n_items * a.g.n10 * sizeof(real)));
+    a.lagflags = (int*)((unsigned char*)workspace + up64((size_t)n_items * score_row_reals(a.g.nfrm) * sizeof(real)));
     if (which & 1) {
         auto ka = align_kernel<false>;
         cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)align_smem());

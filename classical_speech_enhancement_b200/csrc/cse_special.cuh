@@ -101,7 +101,8 @@ CSE_D real2 cse_mmse_bessel_term2(real2 v) {
     const real2 hi = p_mul(poly2(c_M_HI, p_fma(p_rcp(vv), p_set(R(40)), p_set(R(-1.5)))), p_sqrt(vv));
     return mk2(v.x <= R(16) ? lo.x : hi.x, v.y <= R(16) ? lo.y : hi.y);
 }
-CSE_D real2 cse_half_e1_log2_2(real2 v) {
+// enegv = exp(-v) (shared with the speech-presence probability of the caller)
+CSE_D real2 cse_half_e1_log2_2(real2 v, real2 enegv) {
     CSE_POLY_DECL(E_LO);
     CSE_POLY_DECL(E_HI);
     const real2 vl = p_min(v, p_set(R(1)));                         // each branch evaluated inside its own range
@@ -109,6 +110,6 @@ CSE_D real2 cse_half_e1_log2_2(real2 v) {
     const real2 vh = p_max(v, p_set(R(1)));
     const real2 rv = p_rcp(vh);
     const real2 t = p_mul(p_fma(rv, p_set(R(2)), p_set(R(-1.0125))), p_set(R(1.0 / 0.9875)));
-    const real2 hi = p_mul(p_mul(p_set(R(0.5) * CSE_LOG2E), poly2(c_E_HI, t)), p_mul(p_exp2(p_mul(vh, p_set(-CSE_LOG2E))), rv));
+    const real2 hi = p_mul(p_mul(p_set(R(0.5) * CSE_LOG2E), poly2(c_E_HI, t)), p_mul(enegv, rv));
     return mk2(v.x <= R(1) ? lo.x : hi.x, v.y <= R(1) ? lo.y : hi.y);
 }

@@ -124,9 +124,12 @@ CSE_D void gain_pair(real2 Ya, real2 Yb, real2 Nraw, bool first, GainState2& st,
         } else {
             const real gf = pv[2], q = pv[4], vmax = pv[5], lg2gf = pv[6];
             const real2 v = p_clip(p_mul(xr, gam), R(1e-12), vmax);
-            const real2 lg2 = p_add(p_log2(xr), cse_half_e1_log2_2(v));
-            const real2 ql = p_fma(p_set(q), p_mul(p_exp2(p_mul(v, p_set(CSE_LOG2E))), r), p_set(eps));
-            const real2 p = p_clip(p_mul(ql, p_rcp(p_add(ql, p_set(R(1) - q)))), R(0), R(1));
+            const real2 enegv = p_exp2(p_mul(v, p_set(-CSE_LOG2E)));                  // exp(-v)
+            const real2 lg2 = p_add(p_log2(xr), cse_half_e1_log2_2(v, enegv));
+            // p = 1 / (1 + (1-q) / (q Lambda + eps)), Lambda = exp(v)/(1+xi); numerator and denominator
+            // multiplied by exp(-v) so that one exponential serves both E1 and the presence probability
+            const real2 A = p_fma(p_set(eps), enegv, p_mul(p_set(q), r));
+            const real2 p = p_clip(p_mul(A, p_rcp(p_fma(p_set(R(1) - q), enegv, A))), R(0), R(1));
             G = p_clip(p_exp2(p_fma(p, p_add(lg2, p_set(-lg2gf)), p_set(lg2gf))), gf, R(1));
         }
     }
@@ -224,7 +227,6 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
     auto bin_b = [&](int i) { return M - (tid + i * NTB); };
 #pragma unroll
     for (int i = 0; i < PPT; ++i) {
-#pragma unroll
         st[i].g_prev = mk2(R(1), R(1)); st[i].gam_prev = mk2(R(1), R(1)); st[i].nsm = mk2(R(0), R(0));
         nstat[i][0] = (!a.noise_tv && i < n_slots) ? Nu[bin_a(i)] : R(1);
         nstat[i][1] = (!a.noise_tv && is_pair) ? Nu[bin_b(i)] : R(1);

@@ -64,6 +64,9 @@ struct ScoreGeom {
     size_t off_kept, off_need, off_hbmap, off_xtob, off_seg, off_rsum, off_q, bytes;
 };
 
+// reals per candidate of the score workspace: the 15 x (K-1) band envelopes of the STOI kernel
+CSE_HD size_t score_row_reals(int nfrm) { return ((size_t)CSE_NBANDS * (nfrm + 1) + 15) & ~(size_t)15; }
+
 static inline ScoreGeom score_geom(int L) {
     ScoreGeom g;
     g.L = L;
@@ -141,7 +144,7 @@ struct ScoreArgs {
     const real* clean;      // [U][L]
     unsigned char* cache;   // [U] records of geom.bytes
     cse_score_t* scores;    // [n_items]
-    real* y10;              // workspace [n_items][n10]
+    real* y10;              // workspace [n_items][score_row_reals(g)]: band-envelope scratch rows of the STOI kernel
     int* lagflags;          // workspace [n_items][2]
     int per_utt, finalize, item0;   // block b scores global item item0 + b; wav / workspace are chunk-local
     ScoreGeom g;

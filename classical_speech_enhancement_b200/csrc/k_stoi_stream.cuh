@@ -33,7 +33,6 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
     const int u = item / a.per_utt;
     const unsigned char* rec = a.cache + (size_t)u * g.bytes;
     const CleanHeader* hdr = reinterpret_cast<const CleanHeader*>(rec);
-    const int* __restrict__ kept = reinterpret_cast<const int*>(rec + g.off_kept);
     const int* __restrict__ hbmap = reinterpret_cast<const int*>(rec + g.off_hbmap);   // [nfr + 2][3]: jA, jB, count
     const real* __restrict__ xtob = reinterpret_cast<const real*>(rec + g.off_xtob);
     const real* __restrict__ seg_c = reinterpret_cast<const real*>(rec + g.off_seg);
@@ -54,7 +53,7 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
     load_pass_twiddles<8, true>(tws, a.T->tw, tid, NT);
     const real* __restrict__ sig = a.wav + (size_t)li * g.L;
     const real* __restrict__ cl = a.clean + (size_t)u * g.L;
-    real* ytob_g = a.y10 + (size_t)li * g.n10;          // scratch row: 15 * Kf band envelopes (n10 >= 15 Kf)
+    real* ytob_g = a.y10 + (size_t)li * score_row_reals(g.nfrm);   // scratch row: 15 * Kf band envelopes
     const int lag = a.lagflags[2 * li];
     int flags = a.lagflags[2 * li + 1];
     const bool fin = a.finalize != 0;
