@@ -253,3 +253,41 @@ def test_variable_length_pairs_and_full_grid_selection():
     pts, scores, best = oracle.sweep_one_pair(pairs[1][0], pairs[1][1], 16000, oracle.wiener_filter, pr.param_ranges_wiener)
     assert np.abs(sc[1]["stoi"] - np.array([s["stoi"] for s in scores])).max() < TOL_STOI
     assert out["selection"]["wiener"][1]["stoi"]["index"] == best["stoi"]["index"]
+
+
+def test_full_ss_grid_scores_and_argmax():
+    """Full spectral-subtraction grid (720 nominal / 540 unique points) for one pair: every score and the
+    sequential STOI selection against the oracle."""
+    from classical_speech_enhancement_b200.sweep import select_all
+    c, n = make_pair(60, 32000)
+    c, n = f32(c), f32(n)
+    pts = grid.grid_points(pr.param_ranges_ss)
+    seen, scores = {}, []
+    for p in pts:                                   # the oracle is deterministic: reuse duplicates of dead parameters
+        key = (p["alpha"], p["beta"], p["n_fft"], p["hop_length"], p["noise_method"],
+               p["noise_percentile"] if p["noise_method"] == "percentile" else None)
+        if key not in seen:
+            seen[key] = score_candidate(c, oracle.spectral_subtraction(n, 16000, **p), 16000)
+        scores.append(seen[key])
+    best = oracle.select_best(pts, [dict(s, pesq=0.0) for s in scores])
+    eng = engine_for(c, n)
+    sc = eng.sweep("spectralSubtractor", pts)
+    assert eng.last_unique == 540 == len(seen)
+    assert np.abs(sc[0]["stoi"] - np.array([s["stoi"] for s in scores])).max() < TOL_STOI
+    assert np.abs(sc[0]["snr"] - np.array([s["snr"] for s in scores])).max() < TOL_SNR_DB
+    sel = select_all({"spectralSubtractor": sc}, {"spectralSubtractor": pts})["spectralSubtractor"][0]
+    assert sel["stoi"]["index"] == best["stoi"]["index"]
+
+
+def test_random_points_of_the_big_grids():
+    """Random samples of the MMSE and Log-MMSE grids (the full grids cost CPU-hours in the oracle)."""
+    c, n = make_pair(61, 48000)
+    c, n = f32(c), f32(n)
+    eng = engine_for(c, n)
+    rng = np.random.default_rng(5)
+    for alg, ranges, fn in (("mmse", pr.param_ranges_mmse, oracle.mmse), ("omlsa", pr.param_ranges_omlsa, oracle.advanced_mmse)):
+        pts = grid.grid_points(ranges)
+        sc = eng.sweep(alg, pts)[0]
+        for i in rng.choice(len(pts), 24, replace=False):
+            ref = score_candidate(c, fn(n, 16000, **pts[i]), 16000)
+            assert abs(sc[i]["stoi"] - ref["stoi"]) < TOL_STOI and abs(sc[i]["snr"] - ref["snr"]) < TOL_SNR_DB, (alg, pts[i])
