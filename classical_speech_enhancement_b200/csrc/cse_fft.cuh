@@ -42,6 +42,14 @@ template <int m> CSE_D real2 rot8c(real2 d) {   // conj(W_8^m)
 template <bool CONJ> CSE_D real2 twmul(real2 a, real2 w) { return CONJ ? cmulc(a, w) : cmul(a, w); }
 template <int m, bool CONJ> CSE_D real2 rotf(real2 d) { return CONJ ? rot8c<m>(d) : rot8<m>(d); }
 
+// Group index of butterfly slot t in a pass with smallest distance q.  For q == 8 the slots are
+// rotated left by one bit so that the two groups a half-warp touches are 128 elements apart
+// instead of 64: with the storage padding this makes the pass conflict-free (it was 2-way).
+template <int Q, int NGRP> CSE_D int fft_group(int t) {
+    if (Q == 8 && NGRP >= 4) return ((t << 1) & (NGRP - 1)) | (t / (NGRP / 2));
+    return t;
+}
+
 // One pass of RL fused DIF stages (CONJ: conjugated twiddles = inverse transform).  `h` = half size of the first fused stage,
 // q = h >> (RL-1) = smallest butterfly distance of the pass.
 template <int LOG2N, int RL, bool CONJ, int H, int TWN>
@@ -58,7 +66,7 @@ CSE_D void dif_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
     constexpr int coff = 3 * (q - 1) / 7;
     for (int idx = tid; idx < total; idx += nth) {
         const int b = idx / per, r = idx - b * per;
-        const int j = r & (q - 1), grp = r / q;
+        const int j = r & (q - 1), grp = fft_group<q, per / q>(r / q);
         // SIDX(base + m q) == SIDX(base) + SIDX(m q): base = grp*NB*q + j with j < q, q a power of two,
         // so neither the >>4 nor the >>8 term of the padding ever carries across the addition.
         real2* p = s + b * bstride + SIDX(grp * (q * NB) + j);
@@ -110,7 +118,7 @@ CSE_D void dit_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
     constexpr int coff = 3 * (q - 1) / 7;                 // compact layout, see dif_pass
     for (int idx = tid; idx < total; idx += nth) {
         const int b = idx / per, r = idx - b * per;
-        const int j = r & (q - 1), grp = r / q;
+        const int j = r & (q - 1), grp = fft_group<q, per / q>(r / q);
         real2* p = s + b * bstride + SIDX(grp * (q * NB) + j);      // affine storage offsets, see dif_pass
         real2 v[NB];
 #pragma unroll

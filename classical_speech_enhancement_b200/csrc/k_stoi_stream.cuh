@@ -26,7 +26,7 @@
 
 __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
     constexpr int T = CSE_STOI_T, BST = CSE_FFT_STRIDE(256), NK = CSE_STOI_K1 - CSE_STOI_K0, NT = 256;
-    constexpr int H = CSE_RS_A2 / 2, AP2 = H + 17, RB = CSE_STOI_RB, HBT = CSE_STOI_HBT, YT = 5 * CSE_RS_A2;
+    constexpr int H = CSE_RS_A2 / 2, AP2 = H + 18 /* 17 needed; 18 makes the de-interleaving stores 2-way instead of 4-way conflicted */, RB = CSE_STOI_RB, HBT = CSE_STOI_HBT, YT = 5 * CSE_RS_A2;
     CSE_DYN_SMEM(smem_raw);
     const ScoreGeom& g = a.g;
     const int tid = threadIdx.x, li = blockIdx.x, item = a.item0 + li;
