@@ -233,13 +233,39 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
         twc[i] = tw_load(a.T->tw, (is_pair ? tid + i * NTB : 0) * (CSE_TW_N / NFFT));
     }
     auto fetch = [&](int t0) {
+        if (t0 + F <= nf) {
+            // fast path (all F frames exist): running row pointer, compile-time frame offsets
+            const int row0 = t0 * nbp;            // < 2^31: nf <= 8192 frames of <= 1032 bins
+#pragma unroll
+            for (int i = 0; i < PPT; ++i) {
+                if (i < n_slots) {
+                    const real2* __restrict__ pa = Yu + row0 + bin_a(i);
+                    const real* __restrict__ na = Nu + (a.noise_tv ? row0 : 0) + bin_a(i);
+#pragma unroll
+                    for (int f = 0; f < F; ++f) {
+                        yv[i][0][f] = pa[f * nbp];
+                        nv[i][0][f] = a.noise_tv ? na[f * nbp] : nstat[i][0];
+                    }
+                    if (is_pair) {
+                        const real2* __restrict__ pb = Yu + row0 + bin_b(i);
+                        const real* __restrict__ nb_ = Nu + (a.noise_tv ? row0 : 0) + bin_b(i);
+#pragma unroll
+                        for (int f = 0; f < F; ++f) {
+                            yv[i][1][f] = pb[f * nbp];
+                            nv[i][1][f] = a.noise_tv ? nb_[f * nbp] : nstat[i][1];
+                        }
+                    }
+                }
+            }
+            return;
+        }
 #pragma unroll
         for (int i = 0; i < PPT; ++i) {
             const int ka = bin_a(i), kb = bin_b(i);
 #pragma unroll
             for (int f = 0; f < F; ++f) {
                 const int t = t0 + f;
-                const int row = t * nbp;              // < 2^31: nf <= 8192 frames of <= 1032 bins
+                const int row = t * nbp;
                 const bool on = i < n_slots && t < nf;
                 yv[i][0][f] = on ? Yu[row + ka] : mk2(R(0), R(0));
                 nv[i][0][f] = on ? (a.noise_tv ? Nu[row + ka] : nstat[i][0]) : R(1);
@@ -249,6 +275,11 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
             }
         }
     };
+    // lanes without a second bin (the mid lane) keep a harmless dummy in their b half
+#pragma unroll
+    for (int i = 0; i < PPT; ++i)
+#pragma unroll
+        for (int f = 0; f < F; ++f) { yv[i][0][f] = mk2(R(0), R(0)); yv[i][1][f] = mk2(R(0), R(0)); nv[i][0][f] = R(1); nv[i][1][f] = R(1); }
     fetch(0);
 
     // Overlap-add gather plan.  Thread owns window pair-positions jj = tid + k*NT; frame f of an
