@@ -161,6 +161,7 @@ template <int LOG2N> struct EnhanceCfg {
     static constexpr int NT = NTB + 32;                      // + one warp whose lane 0 owns the self-paired bin M/2
     static constexpr int F = (8 * NTB) / M;                  // frames per iteration: F * M/8 butterflies == NTB
     static constexpr int XST = CSE_FFT_STRIDE(M);            // per-frame stride of the packed half-size spectra
+    static constexpr int KMAX = ((NFFT + (F - 1) * (NFFT / 2)) / 2 + NT - 1) / NT;   // overlap-add pair-positions per thread (hop <= n_fft/2)
 };
 
 // One CTA per (utterance, grid point).  Each pair thread owns the bins (s, M-s) of its PPT pair
@@ -285,9 +286,10 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
     // Overlap-add gather plan.  Thread owns window pair-positions jj = tid + k*NT; frame f of an
     // iteration contributes its sample pair m = jj - f*hop/2 (if 0 <= m < M), which sits at a fixed
     // shared-memory offset in the bit-reversed FFT output: all loop-invariant, computed once.
-    constexpr int KMAX = ((NFFT + (F - 1) * (NFFT / 2)) / 2 + NT - 1) / NT;
+    constexpr int KMAX = C::KMAX;
     const int hh = hop >> 1;
-    unsigned zoff[KMAX][(F + 1) / 2];            // two 16-bit offsets per register; 0xffff = no contribution
+    constexpr int F2 = (F + 1) / 2;
+    unsigned* zoff_s = reinterpret_cast<unsigned*>(tws + FftTwLayout<LOG2M, true>::SIZE);   // [KMAX * F2][NT], two 16-bit offsets each
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
         const int jj = tid + k * NT;
@@ -300,8 +302,19 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
                 const unsigned off = (f < F && jj < W / 2 && m >= 0 && m < M) ? (unsigned)(f * XST + SIDX(brev_n(m, LOG2M))) : 0xffffu;
                 packed |= off << (16 * e);
             }
-            zoff[k][f2] = packed;
+            zoff_s[(k * F2 + f2) * NT + tid] = packed;
         }
+    }
+
+    // Steady-state normalisation of the pairs this thread emits (window positions j < F*hop): the
+    // window sum-of-squares only depends on j mod hop there, so 1/(N * wss) is loop-invariant.
+    constexpr int KEMIT = 2;           // pairs tid, tid+NT: all emitted pairs when F*hop/2 <= 2*NT (hop <= n_fft/4 here); wider hops use the general path
+    real2* inv_ws_s = reinterpret_cast<real2*>(zoff_s + KMAX * F2 * NT);      // [KEMIT][NT]
+#pragma unroll
+    for (int k = 0; k < KEMIT; ++k) {
+        const int j = 2 * (tid + k * NT);
+        const int r0 = j % hop, r1 = (j + 1) % hop;
+        inv_ws_s[k * NT + tid] = (j < F * hop) ? mk2(R(1) / ((real)NFFT * wsteady[r0]), R(1) / ((real)NFFT * wsteady[r1])) : mk2(R(0), R(0));
     }
 
     const int total_pos = L + M;             // padded positions [0, L + M) must be emitted
@@ -346,6 +359,8 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
         // is one complex FFT output), emit the F*hop positions no later frame touches
         const int p_begin = t0 * hop;
         const int emit_end = p_begin + F * hop;
+        // steady state: all frames covering the emitted positions exist and the positions map inside [0, L)
+        const bool steady = p_begin >= NFFT && t0 + F <= nf && p_begin >= M && emit_end <= L + M;
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
             const int jj = tid + k * NT;
@@ -356,14 +371,23 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
             real2 acc = *reinterpret_cast<real2*>(ring + slot);
             if (any) {                       // frames beyond n_frames were written as zero spectra
 #pragma unroll
-                for (int f = 0; f < F; ++f) {
-                    const unsigned off = (zoff[k][f >> 1] >> (16 * (f & 1))) & 0xffffu;
-                    if (off != 0xffffu) acc = cfma2(xs[off], w2s[jj - f * hh], acc);
+                for (int f2 = 0; f2 < F2; ++f2) {
+                    const unsigned packed = zoff_s[(k * F2 + f2) * NT + tid];   // own slots: no synchronisation needed
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int f = 2 * f2 + e;
+                        const unsigned off = (packed >> (16 * e)) & 0xffffu;
+                        if (f < F && off != 0xffffu) acc = cfma2(xs[off], w2s[jj - f * hh], acc);
+                    }
                 }
             }
             if (p < emit_end) {
                 const int i = p - M;
-                if (i >= -1 && i < L) {
+                if (steady && vec2 && k < KEMIT) {
+                    // interior of the signal: every covering frame exists, all samples are in range
+                    const real2 iw = inv_ws_s[k * NT + tid];
+                    *reinterpret_cast<real2*>(out + i) = mk2(acc.x * iw.x, acc.y * iw.y);
+                } else if (i >= -1 && i < L) {
                     // window sum-of-squares of the frames covering p and p+1 (librosa window_sumsquare)
                     real ws[2];
 #pragma unroll
