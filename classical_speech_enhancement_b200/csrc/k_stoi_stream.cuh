@@ -69,29 +69,45 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
         // ---- 1. input tile, SNR sums and finite check on the samples this tile owns
         {
             constexpr int TOT = 8 * (CSE_RS_A2 + 17), PERT = (TOT + NT - 1) / NT;
+            static_assert(NT == 256 && H == 256 && PERT == 17, "tile-load index algebra below assumes 256 threads, 512 groups");
             const int j0 = 8 * a0 - 64;
+            const bool interior = lag == 0 && j0 >= 0 && j0 + TOT <= L;      // uniform: no bounds, no shift
             real raw[PERT], cv[PERT];
+            if (interior) {
+                const real* __restrict__ sp = sig + j0 + tid;
+                const real* __restrict__ cp = cl + j0 + tid;
 #pragma unroll
-            for (int k = 0; k < PERT; ++k) {
-                const int jj = tid + k * NT, j = j0 + jj;
-                const bool own = jj >= 64 && jj < 64 + 8 * CSE_RS_A2 && j < L;        // each sample owned by one tile
-                raw[k] = jj < TOT ? xraw(sig, j, lag, L) : R(0);
-                cv[k] = own ? cl[j] : R(0);
-            }
-#pragma unroll
-            for (int k = 0; k < PERT; ++k) {
-                const int jj = tid + k * NT, j = j0 + jj;
-                if (jj < TOT) {
-                    const real v = fin ? r_clip(raw[k], R(-1), R(1)) : raw[k];
-                    if (jj >= 64 && jj < 64 + 8 * CSE_RS_A2 && j < L) {
-                        if (!r_finite(raw[k])) bad = 1;
-                        const real d = cv[k] - v;
-                        pn = r_fma(d, d, pn);
-                    }
-                    const int c = jj & 7, ap = jj >> 3;
-                    if (ap < AP2) xs2[c * AP2 + ap].x = v;
-                    if (ap >= H) xs2[c * AP2 + ap - H].y = v;
+                for (int k = 0; k < PERT; ++k) {
+                    raw[k] = (k < PERT - 1 || tid + k * NT < TOT) ? sp[k * NT] : R(0);
+                    cv[k] = (k >= 1 && k < PERT - 1) || (k == 0 && tid >= 64) || (k == PERT - 1 && tid < 64) ? cp[k * NT] : R(0);
                 }
+            } else {
+#pragma unroll
+                for (int k = 0; k < PERT; ++k) {
+                    const int jj = tid + k * NT, j = j0 + jj;
+                    const bool own = jj >= 64 && jj < 64 + 8 * CSE_RS_A2 && j < L;        // each sample owned by one tile
+                    raw[k] = jj < TOT ? xraw(sig, j, lag, L) : R(0);
+                    cv[k] = own ? cl[j] : R(0);
+                }
+            }
+            // jj = tid + 256 k  ->  c = tid & 7, column ap = (tid >> 3) + 32 k: columns < 256 feed the .x half of
+            // the pair tile, columns >= 256 the .y half (column - 256); the 18 columns of overlap feed both.
+            const int c = tid & 7, ap0 = tid >> 3;
+            real2* row = xs2 + c * AP2 + ap0;
+#pragma unroll
+            for (int k = 0; k < PERT; ++k) {
+                const int jj = tid + k * NT, j = j0 + jj;
+                const real v = fin ? r_clip(raw[k], R(-1), R(1)) : raw[k];
+                const bool own = interior ? ((k >= 1 && k < PERT - 1) || (k == 0 && tid >= 64) || (k == PERT - 1 && tid < 64))
+                                          : (jj >= 64 && jj < 64 + 8 * CSE_RS_A2 && j < L);
+                if (own) {
+                    if (!r_finite(raw[k])) bad = 1;
+                    const real d = cv[k] - v;
+                    pn = r_fma(d, d, pn);
+                }
+                if (k < 8) row[32 * k].x = v;
+                else if (k == 8) { if (ap0 + 256 < AP2) row[256].x = v; row[0].y = v; }
+                else if (k < PERT - 1 || jj < TOT) row[32 * (k - 8)].y = v;
             }
         }
         __syncthreads();
