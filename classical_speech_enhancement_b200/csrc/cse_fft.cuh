@@ -46,13 +46,14 @@ template <int m, bool CONJ> CSE_D real2 rotf(real2 d) { return CONJ ? rot8c<m>(d
 // rotated left by one bit so that the two groups a half-warp touches are 128 elements apart
 // instead of 64: with the storage padding this makes the pass conflict-free (it was 2-way).
 template <int Q, int NGRP> CSE_D int fft_group(int t) {
-    if (Q == 8 && NGRP >= 4) return ((t << 1) & (NGRP - 1)) | (t / (NGRP / 2));
+    if (Q == 8 && NGRP >= 4) return ((t << 1) & (NGRP - 1)) | (t / (NGRP >= 2 ? NGRP / 2 : 1));
     return t;
 }
 
 // One pass of RL fused DIF stages (CONJ: conjugated twiddles = inverse transform).  `h` = half size of the first fused stage,
 // q = h >> (RL-1) = smallest butterfly distance of the pass.
-template <int LOG2N, int RL, bool CONJ, int H, int TWN>
+// ZHI: the upper half of every transform's input is known to be zero (zero-padded frames) and is not read.
+template <int LOG2N, int RL, bool CONJ, int H, int TWN, bool ZHI = false>
 CSE_D void dif_pass(real2* s, int nbatch, int bstride, const real2* __restrict__ tw, int tid, int nth) {
     constexpr int N = 1 << LOG2N;
     constexpr int NB = 1 << RL;               // elements per butterfly
@@ -72,7 +73,7 @@ CSE_D void dif_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
         real2* p = s + b * bstride + SIDX(grp * (q * NB) + j);
         real2 v[NB];
 #pragma unroll
-        for (int m = 0; m < NB; ++m) v[m] = p[SIDX(m * q)];
+        for (int m = 0; m < NB; ++m) v[m] = (ZHI && m >= NB / 2) ? mk2(R(0), R(0)) : p[SIDX(m * q)];
         if (RL == 3) {
             const real2 w1 = TWN > 0 ? tw_load(tw, j * twstep) : tw_load(tw, coff + j);
             const real2 w2 = TWN > 0 ? tw_load(tw, j * twstep * 2) : tw_load(tw, coff + q + j);
@@ -160,7 +161,7 @@ CSE_D void dit_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
 // Decimation-in-frequency transform, natural-order in -> bit-reversed out.  INV=false: forward
 // (e^-j); INV=true: unnormalised inverse (e^+j).  Ends with a __syncthreads().  Stage sizes are
 // template constants so that all index arithmetic folds to shifts and masks.
-template <int LOG2N, bool INV, int TWN = CSE_TW_N>
+template <int LOG2N, bool INV, int TWN = CSE_TW_N, bool ZHI = false>
 CSE_D void fft_dif(real2* s, int nbatch, int bstride, const real2* __restrict__ tw, int tid, int nth,
                    const real2* __restrict__ twg = nullptr) {
     constexpr int REM = LOG2N % 3, NP = LOG2N / 3;
@@ -168,9 +169,9 @@ CSE_D void fft_dif(real2* s, int nbatch, int bstride, const real2* __restrict__ 
     constexpr int TWR = TWN < 0 ? CSE_TW_N : TWN;          // remainder pass: flat global table when TWN == -1
     constexpr int TW3 = TWN < 0 ? 0 : TWN;                 // radix-8 passes: compact when TWN <= 0
     const real2* twr = TWN < 0 ? twg : tw;
-    if constexpr (REM == 1) { dif_pass<LOG2N, 1, INV, H0, TWR>(s, nbatch, bstride, twr, tid, nth); __syncthreads(); }
-    if constexpr (REM == 2) { dif_pass<LOG2N, 2, INV, H0, TWR>(s, nbatch, bstride, twr, tid, nth); __syncthreads(); }
-    if constexpr (NP >= 1) { dif_pass<LOG2N, 3, INV, H1, TW3>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (REM == 1) { dif_pass<LOG2N, 1, INV, H0, TWR, ZHI>(s, nbatch, bstride, twr, tid, nth); __syncthreads(); }
+    if constexpr (REM == 2) { dif_pass<LOG2N, 2, INV, H0, TWR, ZHI>(s, nbatch, bstride, twr, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 1) { dif_pass<LOG2N, 3, INV, H1, TW3, (ZHI && REM == 0)>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
     if constexpr (NP >= 2) { dif_pass<LOG2N, 3, INV, (H1 >> 3), TW3>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
     if constexpr (NP >= 3) { dif_pass<LOG2N, 3, INV, (H1 >> 6), TW3>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
     if constexpr (NP >= 4) { dif_pass<LOG2N, 3, INV, (H1 >> 9), TW3>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }

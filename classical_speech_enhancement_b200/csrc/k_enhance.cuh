@@ -150,6 +150,9 @@ struct EnhanceArgs {
     real eps;
 };
 
+#ifndef CSE_ENH_MB_SMALL
+#define CSE_ENH_MB_SMALL 4    // resident CTAs per SM asked of ptxas for the <= 200-thread variants (n_fft <= 512)
+#endif
 #ifndef CSE_ENH_CAP
 #define CSE_ENH_CAP 256
 #endif
@@ -170,7 +173,7 @@ template <int LOG2N> struct EnhanceCfg {
 // so it is formed in registers and written straight into the FFT buffer - no separate split
 // pass, no exchange through shared memory.
 template <int ALG, int LOG2N>
-__global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT > 200 ? 3 : 4)) enhance_kernel(EnhanceArgs a) {
+__global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT > 200 ? 3 : CSE_ENH_MB_SMALL)) enhance_kernel(EnhanceArgs a) {
     typedef EnhanceCfg<LOG2N> C;
     constexpr int NFFT = C::NFFT, M = C::M, LOG2M = LOG2N - 1, NTB = C::NTB, PPT = C::PPT, NT = C::NT, F = C::F;
     constexpr int XST = C::XST;

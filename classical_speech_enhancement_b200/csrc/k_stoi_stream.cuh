@@ -46,11 +46,36 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
     real* ring = yt + YT;                                                     // RB * 128
     real* w_s = ring + RB * 128;                                              // 256
     real2* tws = reinterpret_cast<real2*>(w_s + 256);                         // 160
+    real2* ktw_s = tws + 160;                                                 // NK: W_512^k of the real-FFT split
+    unsigned* koff_s = reinterpret_cast<unsigned*>(ktw_s + NK);               // NK: storage offsets of bins k | 256-k
     real2* xs2 = fbuf;
     real* pw = yt;
 
     for (int i = tid; i < 256; i += NT) w_s[i] = a.T->stoi_win[i];
     load_pass_twiddles<8, true>(tws, a.T->tw, tid, NT);
+    for (int i = tid; i < NK; i += NT) {
+        const int k = CSE_STOI_K0 + i;
+        ktw_s[i] = tw_load(a.T->tw, k * (CSE_TW_N / 512));
+        koff_s[i] = (unsigned)SIDX(brev_n(k, 8)) | ((unsigned)SIDX(brev_n(256 - k, 8)) << 16);
+    }
+    // Band sums are done by one warp per frame: lane = a run of <= 9 consecutive bins inside one
+    // band (29 runs cover the 15 bands); the first lane of a band adds its neighbours' partials.
+    // The run descriptor (first bin | length << 8 | band << 12 | runs of the band if first << 16) sits in shared memory.
+    static_assert(T * 32 == NT, "one warp per frame of a batch");
+    unsigned* run_s = koff_s + NK;                                            // 32
+    if (tid < 32) {
+        unsigned desc = 0;
+        int r0 = 0;
+        for (int b = 0; b < CSE_NBANDS; ++b) {
+            const int e0 = a.T->stoi_edges[b], wd = a.T->stoi_edges[b + 1] - e0, n = (wd + 8) / 9;
+            if (tid >= r0 && tid < r0 + n) {
+                const int i = tid - r0, lo = (i * wd) / n, hi = ((i + 1) * wd) / n;
+                desc = (unsigned)(e0 + lo - CSE_STOI_K0) | ((unsigned)(hi - lo) << 8) | ((unsigned)b << 12) | ((unsigned)(i == 0 ? n : 0) << 16);
+            }
+            r0 += n;
+        }
+        run_s[tid] = desc;
+    }
     const real* __restrict__ sig = a.wav + (size_t)li * g.L;
     const real* __restrict__ cl = a.clean + (size_t)u * g.L;
     real* ytob_g = a.y10 + (size_t)li * score_row_reals(g.nfrm);   // scratch row: 15 * Kf band envelopes
@@ -64,7 +89,6 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
     real pn = R(0);
     int bad = 0, m_next = 0;
     const int na = (n10 + 4) / 5;
-    const int* __restrict__ edges = a.T->stoi_edges;
     for (int a0 = 0, t = 0; a0 < na; a0 += CSE_RS_A2, ++t) {
         // ---- 1. input tile, SNR sums and finite check on the samples this tile owns
         {
@@ -176,28 +200,39 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
                     const real* B = ring + (j & (RB - 1)) * 128;
                     v = mk2(w_s[n] * B[nn], w_s[n + 1] * B[nn + 1]);
                 }
-                fbuf[f * BST + SIDX(mm)] = v;
-                fbuf[f * BST + SIDX(mm + 128)] = mk2(R(0), R(0));
+                fbuf[f * BST + SIDX(mm)] = v;          // upper half of the zero-padded frame: never stored, the first pass knows
             }
             __syncthreads();
-            fft_dif<8, false, 0>(fbuf, T, BST, tws, tid, NT);
-            for (int idx = tid; idx < T * NK; idx += NT) {
-                const int f = idx / NK, k = CSE_STOI_K0 + (idx - f * NK);
-                const real2* zf = fbuf + f * BST;
-                const real2 z0 = zf[SIDX(brev_n(k, 8))], z1 = zf[SIDX(brev_n(256 - k, 8))];
-                const real2 E = mk2(R(0.5) * (z0.x + z1.x), R(0.5) * (z0.y - z1.y));
-                const real2 O = mk2(R(0.5) * (z0.y + z1.y), R(-0.5) * (z0.x - z1.x));
-                const real2 X = cadd(E, cmul(O, tw_load(a.T->tw, k * (CSE_TW_N / 512))));
-                pw[idx] = X.x * X.x + X.y * X.y;
-            }
-            __syncthreads();
-            for (int idx = tid; idx < T * CSE_NBANDS; idx += NT) {
-                const int f = idx / CSE_NBANDS, b = idx - f * CSE_NBANDS, m = m0 + f;
-                if (m < Kf) {
-                    real sacc = R(0);
-                    for (int k = edges[b]; k < edges[b + 1]; ++k) sacc += pw[f * NK + k - CSE_STOI_K0];
-                    ytob_g[b * Kf + m] = r_sqrt(sacc);
+            fft_dif<8, false, 0, true>(fbuf, T, BST, tws, tid, NT);
+            {
+                const int lane = tid & 31, wf = tid >> 5;
+                const unsigned desc = run_s[lane];
+                const int run_lo = desc & 0xff, run_len = (desc >> 8) & 0xf, run_band = (desc >> 12) & 0xf, run_lead = desc >> 16;
+                const real2* zf = fbuf + wf * BST;
+                real* pwf = pw + wf * NK;
+#pragma unroll
+                for (int c = 0; c < (NK + 31) / 32; ++c) {
+                    const int i = lane + 32 * c;
+                    if (i < NK) {
+                        const unsigned off = koff_s[i];
+                        const real2 z0 = zf[off & 0xffffu], z1 = zf[off >> 16];
+                        const real2 E = mk2(R(0.5) * (z0.x + z1.x), R(0.5) * (z0.y - z1.y));
+                        const real2 O = mk2(R(0.5) * (z0.y + z1.y), R(-0.5) * (z0.x - z1.x));
+                        const real2 X = cadd(E, cmul(O, ktw_s[i]));
+                        pwf[i] = X.x * X.x + X.y * X.y;
+                    }
                 }
+                __syncwarp();
+                real sacc = R(0);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) if (i < run_len) sacc += pwf[run_lo + i];
+#pragma unroll
+                for (int d = 1; d < 5; ++d) {
+                    const real o = __shfl_down_sync(0xffffffffu, sacc, d);
+                    if (d < run_lead) sacc += o;
+                }
+                const int m = m0 + wf;
+                if (run_lead > 0 && m < Kf) ytob_g[run_band * Kf + m] = r_sqrt(sacc);
             }
             __syncthreads();
             m_next += T;
@@ -226,29 +261,35 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
     __threadfence_block();
     __syncthreads();
     real* ysm = reinterpret_cast<real*>(fbuf);
-    const bool fits = CSE_NBANDS * Kf <= 2 * T * BST + YT + RB * 128;      // fbuf + yt + ring are free now
+    const int nenv = CSE_NBANDS * Kf;
+    const bool fits = 2 * nenv <= 2 * T * BST + YT + RB * 128;              // fbuf + yt + ring are free now
     if (fits) {
-        for (int i = tid; i < CSE_NBANDS * Kf; i += NT) ysm[i] = ytob_g[i];
+        for (int i = tid; i < nenv; i += NT) { ysm[i] = ytob_g[i]; ysm[nenv + i] = xtob[i]; }
         __syncthreads();
     }
     const real* ytob = fits ? ysm : ytob_g;
+    const real* xenv = fits ? ysm + nenv : xtob;
     const real EPS = R(2.220446049250313e-16);
     const real clipc = R(1) + R(5.623413251903491);
     real dsum = R(0);
     for (int idx = tid; idx < J * CSE_NBANDS; idx += NT) {
         const int b = idx / J, j = idx - b * J;
-        const real* x = xtob + b * Kf + j;
+        const real* x = xenv + b * Kf + j;
         const real* y = ytob + b * Kf + j;
         const real xn = seg_c[idx], xmean = seg_c[(size_t)J * CSE_NBANDS + idx], xinv = seg_c[(size_t)2 * J * CSE_NBANDS + idx];
+        real yr[CSE_NSEG];                                                  // the segment stays in registers
         real y2 = R(0);
-        for (int n = 0; n < CSE_NSEG; ++n) y2 = r_fma(y[n], y[n], y2);
+#pragma unroll
+        for (int n = 0; n < CSE_NSEG; ++n) { yr[n] = y[n]; y2 = r_fma(yr[n], yr[n], y2); }
         const real alpha = xn / (r_sqrt(y2) + EPS);
         real s1 = R(0);
-        for (int n = 0; n < CSE_NSEG; ++n) s1 += r_min(alpha * y[n], clipc * x[n]);
+#pragma unroll
+        for (int n = 0; n < CSE_NSEG; ++n) { yr[n] = r_min(alpha * yr[n], clipc * x[n]); s1 += yr[n]; }
         const real ymean = s1 / R(CSE_NSEG);
         real c2 = R(0), cx = R(0);
+#pragma unroll
         for (int n = 0; n < CSE_NSEG; ++n) {
-            const real d = r_min(alpha * y[n], clipc * x[n]) - ymean;
+            const real d = yr[n] - ymean;
             c2 = r_fma(d, d, c2);
             cx = r_fma(d, x[n] - xmean, cx);
         }
