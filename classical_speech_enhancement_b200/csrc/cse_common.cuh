@@ -80,6 +80,12 @@ CSE_HD real r_fma(real a, real b, real c) { return fmaf(a, b, c); }
 // relative error <= ~2e-7 .. 1e-6 over the ranges the gain rules use - far inside the 1e-4
 // waveform budget; no argument here is ever denormal).  The FP64 build and the CPU emulation use
 // the exact forms.
+// Hint: pull the 128-byte line at p into L2 (no register, no dependency); nothing under the emulator.
+#if defined(CSE_EMU)
+CSE_D void cse_prefetch_l2(const void*) {}
+#else
+CSE_D void cse_prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#endif
 #if defined(CSE_FP64) || defined(CSE_EMU)
 CSE_HD real r_rcp(real x) { return R(1) / x; }
 CSE_HD real r_fexp2(real x) { return (real)exp2((double)x); }

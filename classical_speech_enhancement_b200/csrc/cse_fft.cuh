@@ -39,8 +39,41 @@ template <int m> CSE_D real2 rot8c(real2 d) {   // conj(W_8^m)
     return cscale(cadd(mk2(-d.x, -d.y), mk2(-d.y, d.x)), h);       // * (-1 + i)/sqrt2
 }
 
-template <bool CONJ> CSE_D real2 twmul(real2 a, real2 w) { return CONJ ? cmulc(a, w) : cmul(a, w); }
+// UNIT: the twiddle is known to be 1 (every twiddle of the q == 1 pass): no load, no multiply, same bits.
+template <bool CONJ, bool UNIT = false> CSE_D real2 twmul(real2 a, real2 w) { return UNIT ? a : (CONJ ? cmulc(a, w) : cmul(a, w)); }
 template <int m, bool CONJ> CSE_D real2 rotf(real2 d) { return CONJ ? rot8c<m>(d) : rot8<m>(d); }
+
+// Three fused radix-2 stages on 8 register values.  DIF: distances 4, 2, 1 with twiddles w1 = W_{8q}^j,
+// w2 = W_{4q}^j, w3 = W_{2q}^j applied after the subtraction; DIT: the mirror image (distances 1, 2, 4,
+// twiddles applied before the butterfly).
+template <bool CONJ, bool U1> CSE_D void bfly8_dif(real2* v, real2 w1, real2 w2, real2 w3) {
+    real2 d;
+    d = csub(v[0], v[4]); v[0] = cadd(v[0], v[4]); v[4] = twmul<CONJ, U1>(rotf<0, CONJ>(d), w1);
+    d = csub(v[1], v[5]); v[1] = cadd(v[1], v[5]); v[5] = twmul<CONJ, U1>(rotf<1, CONJ>(d), w1);
+    d = csub(v[2], v[6]); v[2] = cadd(v[2], v[6]); v[6] = twmul<CONJ, U1>(rotf<2, CONJ>(d), w1);
+    d = csub(v[3], v[7]); v[3] = cadd(v[3], v[7]); v[7] = twmul<CONJ, U1>(rotf<3, CONJ>(d), w1);
+#pragma unroll
+    for (int g = 0; g < 8; g += 4) {
+        d = csub(v[g], v[g + 2]); v[g] = cadd(v[g], v[g + 2]); v[g + 2] = twmul<CONJ, U1>(d, w2);
+        d = csub(v[g + 1], v[g + 3]); v[g + 1] = cadd(v[g + 1], v[g + 3]); v[g + 3] = twmul<CONJ, U1>(rotf<2, CONJ>(d), w2);
+    }
+#pragma unroll
+    for (int g = 0; g < 8; g += 2) { d = csub(v[g], v[g + 1]); v[g] = cadd(v[g], v[g + 1]); v[g + 1] = twmul<CONJ, U1>(d, w3); }
+}
+template <bool CONJ, bool U1> CSE_D void bfly8_dit(real2* v, real2 w1, real2 w2, real2 w3) {
+    real2 t;
+#pragma unroll
+    for (int g = 0; g < 8; g += 2) { t = twmul<CONJ, U1>(v[g + 1], w3); v[g + 1] = csub(v[g], t); v[g] = cadd(v[g], t); }
+#pragma unroll
+    for (int g = 0; g < 8; g += 4) {
+        t = twmul<CONJ, U1>(v[g + 2], w2); v[g + 2] = csub(v[g], t); v[g] = cadd(v[g], t);
+        t = rotf<2, CONJ>(twmul<CONJ, U1>(v[g + 3], w2)); v[g + 3] = csub(v[g + 1], t); v[g + 1] = cadd(v[g + 1], t);
+    }
+    t = rotf<0, CONJ>(twmul<CONJ, U1>(v[4], w1)); v[4] = csub(v[0], t); v[0] = cadd(v[0], t);
+    t = rotf<1, CONJ>(twmul<CONJ, U1>(v[5], w1)); v[5] = csub(v[1], t); v[1] = cadd(v[1], t);
+    t = rotf<2, CONJ>(twmul<CONJ, U1>(v[6], w1)); v[6] = csub(v[2], t); v[2] = cadd(v[2], t);
+    t = rotf<3, CONJ>(twmul<CONJ, U1>(v[7], w1)); v[7] = csub(v[3], t); v[3] = cadd(v[3], t);
+}
 
 // Group index of butterfly slot t in a pass with smallest distance q.  For q == 8 the slots are
 // rotated left by one bit so that the two groups a half-warp touches are 128 elements apart
@@ -61,6 +94,7 @@ CSE_D void dif_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
     constexpr int q = h >> (RL - 1);
     constexpr int per = N / NB;
     const int total = nbatch * per;
+    constexpr bool U1 = q == 1;                  // all twiddles of this pass are W^0
     // TWN > 0: `tw` is a flat table W_TWN^k.  TWN == 0: `tw` is the compact per-pass layout of
     // load_pass_twiddles (block of this pass at 3(q-1)/7: [W_{8q}^j | W_{4q}^j | W_{2q}^j], unit stride).
     constexpr int twstep = TWN > 0 ? (TWN / 2) / h : 0;
@@ -75,32 +109,21 @@ CSE_D void dif_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
 #pragma unroll
         for (int m = 0; m < NB; ++m) v[m] = (ZHI && m >= NB / 2) ? mk2(R(0), R(0)) : p[SIDX(m * q)];
         if (RL == 3) {
-            const real2 w1 = TWN > 0 ? tw_load(tw, j * twstep) : tw_load(tw, coff + j);
-            const real2 w2 = TWN > 0 ? tw_load(tw, j * twstep * 2) : tw_load(tw, coff + q + j);
-            const real2 w3 = TWN > 0 ? tw_load(tw, j * twstep * 4) : tw_load(tw, coff + 2 * q + j);
-            real2 d;
-            d = csub(v[0], v[4]); v[0] = cadd(v[0], v[4]); v[4] = twmul<CONJ>(rotf<0, CONJ>(d), w1);
-            d = csub(v[1], v[5]); v[1] = cadd(v[1], v[5]); v[5] = twmul<CONJ>(rotf<1, CONJ>(d), w1);
-            d = csub(v[2], v[6]); v[2] = cadd(v[2], v[6]); v[6] = twmul<CONJ>(rotf<2, CONJ>(d), w1);
-            d = csub(v[3], v[7]); v[3] = cadd(v[3], v[7]); v[7] = twmul<CONJ>(rotf<3, CONJ>(d), w1);
-#pragma unroll
-            for (int g = 0; g < 8; g += 4) {
-                d = csub(v[g], v[g + 2]); v[g] = cadd(v[g], v[g + 2]); v[g + 2] = twmul<CONJ>(d, w2);
-                d = csub(v[g + 1], v[g + 3]); v[g + 1] = cadd(v[g + 1], v[g + 3]); v[g + 3] = twmul<CONJ>(rotf<2, CONJ>(d), w2);
-            }
-#pragma unroll
-            for (int g = 0; g < 8; g += 2) { d = csub(v[g], v[g + 1]); v[g] = cadd(v[g], v[g + 1]); v[g + 1] = twmul<CONJ>(d, w3); }
+            const real2 w1 = U1 ? mk2(R(1), R(0)) : TWN > 0 ? tw_load(tw, j * twstep) : tw_load(tw, coff + j);
+            const real2 w2 = U1 ? mk2(R(1), R(0)) : TWN > 0 ? tw_load(tw, j * twstep * 2) : tw_load(tw, coff + q + j);
+            const real2 w3 = U1 ? mk2(R(1), R(0)) : TWN > 0 ? tw_load(tw, j * twstep * 4) : tw_load(tw, coff + 2 * q + j);
+            bfly8_dif<CONJ, U1>(v, w1, w2, w3);
         } else if (RL == 2) {
-            const real2 w1 = TWN > 0 ? tw_load(tw, j * twstep) : tw_load(tw, coff + j);
-            const real2 w2 = TWN > 0 ? tw_load(tw, j * twstep * 2) : tw_load(tw, coff + q + j);
+            const real2 w1 = U1 ? mk2(R(1), R(0)) : TWN > 0 ? tw_load(tw, j * twstep) : tw_load(tw, coff + j);
+            const real2 w2 = U1 ? mk2(R(1), R(0)) : TWN > 0 ? tw_load(tw, j * twstep * 2) : tw_load(tw, coff + q + j);
             real2 d;
-            d = csub(v[0], v[2]); v[0] = cadd(v[0], v[2]); v[2] = twmul<CONJ>(d, w1);
-            d = csub(v[1], v[3]); v[1] = cadd(v[1], v[3]); v[3] = twmul<CONJ>(rotf<2, CONJ>(d), w1);
-            d = csub(v[0], v[1]); v[0] = cadd(v[0], v[1]); v[1] = twmul<CONJ>(d, w2);
-            d = csub(v[2], v[3]); v[2] = cadd(v[2], v[3]); v[3] = twmul<CONJ>(d, w2);
+            d = csub(v[0], v[2]); v[0] = cadd(v[0], v[2]); v[2] = twmul<CONJ, U1>(d, w1);
+            d = csub(v[1], v[3]); v[1] = cadd(v[1], v[3]); v[3] = twmul<CONJ, U1>(rotf<2, CONJ>(d), w1);
+            d = csub(v[0], v[1]); v[0] = cadd(v[0], v[1]); v[1] = twmul<CONJ, U1>(d, w2);
+            d = csub(v[2], v[3]); v[2] = cadd(v[2], v[3]); v[3] = twmul<CONJ, U1>(d, w2);
         } else {
-            const real2 w1 = TWN > 0 ? tw_load(tw, j * twstep) : tw_load(tw, coff + j);
-            real2 d = csub(v[0], v[1]); v[0] = cadd(v[0], v[1]); v[1] = twmul<CONJ>(d, w1);
+            const real2 w1 = U1 ? mk2(R(1), R(0)) : TWN > 0 ? tw_load(tw, j * twstep) : tw_load(tw, coff + j);
+            real2 d = csub(v[0], v[1]); v[0] = cadd(v[0], v[1]); v[1] = twmul<CONJ, U1>(d, w1);
         }
 #pragma unroll
         for (int m = 0; m < NB; ++m) p[SIDX(m * q)] = v[m];
@@ -115,6 +138,7 @@ CSE_D void dit_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
     constexpr int q = Q;
     constexpr int per = N / NB;
     const int total = nbatch * per;
+    constexpr bool U1 = q == 1;                  // all twiddles of this pass are W^0
     constexpr int twq = TWN > 0 ? (TWN / 2) / q : 0;     // W_{2q}^p = W_T^{p * T/(2q)}
     constexpr int coff = 3 * (q - 1) / 7;                 // compact layout, see dif_pass
     for (int idx = tid; idx < total; idx += nth) {
@@ -126,32 +150,21 @@ CSE_D void dit_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
         for (int m = 0; m < NB; ++m) v[m] = p[SIDX(m * q)];
         if (RL == 3) {
             // distances q (W_{2q}^j), 2q (W_{4q}^{j + (m&1)q}), 4q (W_{8q}^{j + (m&3)q}); conjugated
-            const real2 w3 = TWN > 0 ? tw_load(tw, j * twq) : tw_load(tw, coff + 2 * q + j);
-            const real2 w2 = TWN > 0 ? tw_load(tw, j * (twq >> 1)) : tw_load(tw, coff + q + j);
-            const real2 w1 = TWN > 0 ? tw_load(tw, j * (twq >> 2)) : tw_load(tw, coff + j);
-            real2 t;
-#pragma unroll
-            for (int g = 0; g < 8; g += 2) { t = twmul<CONJ>(v[g + 1], w3); v[g + 1] = csub(v[g], t); v[g] = cadd(v[g], t); }
-#pragma unroll
-            for (int g = 0; g < 8; g += 4) {
-                t = twmul<CONJ>(v[g + 2], w2); v[g + 2] = csub(v[g], t); v[g] = cadd(v[g], t);
-                t = rotf<2, CONJ>(twmul<CONJ>(v[g + 3], w2)); v[g + 3] = csub(v[g + 1], t); v[g + 1] = cadd(v[g + 1], t);
-            }
-            t = rotf<0, CONJ>(twmul<CONJ>(v[4], w1)); v[4] = csub(v[0], t); v[0] = cadd(v[0], t);
-            t = rotf<1, CONJ>(twmul<CONJ>(v[5], w1)); v[5] = csub(v[1], t); v[1] = cadd(v[1], t);
-            t = rotf<2, CONJ>(twmul<CONJ>(v[6], w1)); v[6] = csub(v[2], t); v[2] = cadd(v[2], t);
-            t = rotf<3, CONJ>(twmul<CONJ>(v[7], w1)); v[7] = csub(v[3], t); v[3] = cadd(v[3], t);
+            const real2 w3 = U1 ? mk2(R(1), R(0)) : TWN > 0 ? tw_load(tw, j * twq) : tw_load(tw, coff + 2 * q + j);
+            const real2 w2 = U1 ? mk2(R(1), R(0)) : TWN > 0 ? tw_load(tw, j * (twq >> 1)) : tw_load(tw, coff + q + j);
+            const real2 w1 = U1 ? mk2(R(1), R(0)) : TWN > 0 ? tw_load(tw, j * (twq >> 2)) : tw_load(tw, coff + j);
+            bfly8_dit<CONJ, U1>(v, w1, w2, w3);
         } else if (RL == 2) {
-            const real2 w2 = TWN > 0 ? tw_load(tw, j * twq) : tw_load(tw, coff + q + j);
-            const real2 w1 = TWN > 0 ? tw_load(tw, j * (twq >> 1)) : tw_load(tw, coff + j);
+            const real2 w2 = U1 ? mk2(R(1), R(0)) : TWN > 0 ? tw_load(tw, j * twq) : tw_load(tw, coff + q + j);
+            const real2 w1 = U1 ? mk2(R(1), R(0)) : TWN > 0 ? tw_load(tw, j * (twq >> 1)) : tw_load(tw, coff + j);
             real2 t;
-            t = twmul<CONJ>(v[1], w2); v[1] = csub(v[0], t); v[0] = cadd(v[0], t);
-            t = twmul<CONJ>(v[3], w2); v[3] = csub(v[2], t); v[2] = cadd(v[2], t);
-            t = twmul<CONJ>(v[2], w1); v[2] = csub(v[0], t); v[0] = cadd(v[0], t);
-            t = rotf<2, CONJ>(twmul<CONJ>(v[3], w1)); v[3] = csub(v[1], t); v[1] = cadd(v[1], t);
+            t = twmul<CONJ, U1>(v[1], w2); v[1] = csub(v[0], t); v[0] = cadd(v[0], t);
+            t = twmul<CONJ, U1>(v[3], w2); v[3] = csub(v[2], t); v[2] = cadd(v[2], t);
+            t = twmul<CONJ, U1>(v[2], w1); v[2] = csub(v[0], t); v[0] = cadd(v[0], t);
+            t = rotf<2, CONJ>(twmul<CONJ, U1>(v[3], w1)); v[3] = csub(v[1], t); v[1] = cadd(v[1], t);
         } else {
-            const real2 w1 = TWN > 0 ? tw_load(tw, j * twq) : tw_load(tw, coff + j);
-            real2 t = twmul<CONJ>(v[1], w1); v[1] = csub(v[0], t); v[0] = cadd(v[0], t);
+            const real2 w1 = U1 ? mk2(R(1), R(0)) : TWN > 0 ? tw_load(tw, j * twq) : tw_load(tw, coff + j);
+            real2 t = twmul<CONJ, U1>(v[1], w1); v[1] = csub(v[0], t); v[0] = cadd(v[0], t);
         }
 #pragma unroll
         for (int m = 0; m < NB; ++m) p[SIDX(m * q)] = v[m];

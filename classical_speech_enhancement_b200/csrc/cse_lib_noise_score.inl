@@ -82,7 +82,7 @@ static size_t stoi_smem(const ScoreGeom& g) {      // clean_stoi_kernel
 static size_t stoi_stream_smem() {
     return 40 * sizeof(double) + sizeof(real) * ((size_t)CSE_STOI_T * CSE_FFT_STRIDE(256) * 2 + 5 * CSE_RS_A2 +
                                                  (size_t)CSE_STOI_RB * 128 + 256 + 320 +
-                                                 (size_t)3 * (CSE_STOI_K1 - CSE_STOI_K0) + 32);   // + split twiddles (2 reals) and bin offsets per band bin, run descriptors
+                                                 (size_t)3 * (CSE_STOI_K1 - CSE_STOI_K0) + 32 + 128);   // + split twiddles (2 reals) and bin offsets per band bin, run descriptors, hop-block rows of the tile
 }
 static size_t up64(size_t x) { return (x + 63) & ~(size_t)63; }
 static int check_sr(int sr) {

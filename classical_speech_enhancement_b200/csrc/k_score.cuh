@@ -194,41 +194,27 @@ __global__ void __launch_bounds__(512, 2) align_kernel(ScoreArgs a) {
     }
     if (CLEAN && Nc < 256) return;
 
-    real2 acc[PER];
-#pragma unroll
-    for (int k = 0; k < PER; ++k) acc[k] = mk2(R(0), R(0));
     const real meanr = (real)mean;
-    for (int pair = 0; pair < g.npairs; ++pair) {
-        const int b1 = 2 * pair, b2 = b1 + 1;
-        for (int idx = tid; idx < P; idx += NT) {
-            real re, im;
-            if (CLEAN) {        // clean blocks, 2*M samples longer, zero outside [0, Nc)
-                const int n1 = b1 * B - M + idx, n2 = b2 * B - M + idx;
-                re = (n1 >= 0 && n1 < Nc) ? sig[n1] - meanr : R(0);
-                im = (b2 < g.nblocks && n2 >= 0 && n2 < Nc) ? sig[n2] - meanr : R(0);
-            } else {
-                const int n1 = b1 * B + idx, n2 = b2 * B + idx;
-                re = (idx < B && n1 < Nc) ? sig[n1] : R(0);
-                im = (idx < B && b2 < g.nblocks && n2 < Nc) ? sig[n2] : R(0);
-            }
-            z[SIDX(idx)] = mk2(re, im);
-        }
-        __syncthreads();
-        fft_dif<CSE_CORR_LOG2P, false, -1>(z, 1, 0, tws, tid, NT, a.T->tw);
-        if (CLEAN) {
-            for (int idx = tid; idx < P; idx += NT) Q[(size_t)pair * P + idx] = z[SIDX(idx)];
-        } else {
-#pragma unroll
-            for (int k = 0; k < PER; ++k) {
-                const int idx = tid + k * NT;
-                const real2 q = Q[(size_t)pair * P + idx];
-                const real2 c = cmulc(q, z[SIDX(idx)]);
-                acc[k] = cadd(acc[k], c);
-            }
-        }
-        __syncthreads();
-    }
     if (CLEAN) {
+        for (int pair = 0; pair < g.npairs; ++pair) {
+            const int b1 = 2 * pair, b2 = b1 + 1;
+            for (int idx = tid; idx < P; idx += NT) {
+                // clean blocks, 2*M samples longer, zero outside [0, Nc)
+                const int n1 = b1 * B - M + idx, n2 = b2 * B - M + idx;
+                const real re = (n1 >= 0 && n1 < Nc) ? sig[n1] - meanr : R(0);
+                const real im = (b2 < g.nblocks && n2 >= 0 && n2 < Nc) ? sig[n2] - meanr : R(0);
+                z[SIDX(idx)] = mk2(re, im);
+            }
+            __syncthreads();
+            fft_dif<CSE_CORR_LOG2P, false, -1>(z, 1, 0, tws, tid, NT, a.T->tw);
+            // stored in the order the candidate side consumes it: thread t of group half gi multiplies
+            // outputs (t + gi NT) 8 + m, m < 8, so slot ((gi 8 + m) NT + t) keeps a warp's reads contiguous
+            for (int idx = tid; idx < P; idx += NT) {
+                const int grp = idx >> 3, m = idx & 7, gi = grp / NT, t = grp - gi * NT;
+                Q[(size_t)pair * P + (gi * 8 + m) * NT + t] = z[SIDX(idx)];
+            }
+            __syncthreads();
+        }
         // rsum[k + M] = sum of clean0[m] over the m that lag k overlaps with (for the mean correction)
         double t0 = 0.0;
         for (int i = tid; i < Nc; i += NT) t0 += (double)(sig[i] - meanr);
@@ -242,16 +228,79 @@ __global__ void __launch_bounds__(512, 2) align_kernel(ScoreArgs a) {
         }
         return;
     }
+
+    // Candidate side.  The 8192-point transform (13 stages = radix 2 x four radix-8 passes) never runs
+    // a pass that only moves data: the first radix-2 stage is applied while the block pair is loaded
+    // (its upper inputs are zero beyond B - P/2), the last forward pass multiplies its register outputs
+    // by the cached clean spectrum and accumulates over block pairs in registers, the first inverse
+    // pass starts from those registers, and the last inverse stage is evaluated only for the
+    // 2 maxlag + 1 lags that are searched.
+    static_assert(CSE_CORR_LOG2P == 13 && PER == 16, "pass structure below: 2 x 8 x 8 x 8 x 8, two radix-8 groups per thread");
+    constexpr int HP = P / 2, ZH = SIDX(HP);
+    const real2* __restrict__ twg = a.T->tw;                  // flat W_8192^k, k < 4096
+    real2 acc[2][8];
 #pragma unroll
-    for (int k = 0; k < PER; ++k) z[SIDX(tid + k * NT)] = acc[k];
+    for (int gi = 0; gi < 2; ++gi)
+#pragma unroll
+        for (int m = 0; m < 8; ++m) acc[gi][m] = mk2(R(0), R(0));
+    for (int pair = 0; pair < g.npairs; ++pair) {
+        const int b1 = 2 * pair, b2 = b1 + 1;
+        const real* __restrict__ s1 = sig + b1 * B;
+        const real* __restrict__ s2 = sig + b2 * B;
+        const int r1 = Nc - b1 * B, r2 = b2 < g.nblocks ? Nc - b2 * B : 0;      // samples left in each block
+        {   // the next pair's samples start their way from DRAM now (one 128-byte line per thread)
+            const int pf = (b1 + 2) * B + tid * (128 / (int)sizeof(real));
+            if (pf < Nc && pf < (b1 + 4) * B) cse_prefetch_l2(sig + pf);
+        }
+#pragma unroll
+        for (int k = 0; k < HP / NT; ++k) {
+            const int i = tid + k * NT, ih = i + HP;
+            const real2 lo = mk2(i < r1 ? s1[i] : R(0), i < r2 ? s2[i] : R(0));            // i < HP < B
+            real2 hi = mk2(R(0), R(0));
+            if (k * NT < B - HP && ih < B) hi = mk2(ih < r1 ? s1[ih] : R(0), ih < r2 ? s2[ih] : R(0));
+            real2* pz = z + SIDX(i);
+            pz[0] = cadd(lo, hi);
+            pz[ZH] = cmul(csub(lo, hi), twg[i]);
+        }
+        __syncthreads();
+        dif_pass<CSE_CORR_LOG2P, 3, false, (HP >> 1), 0>(z, 1, 0, tws, tid, NT); __syncthreads();
+        dif_pass<CSE_CORR_LOG2P, 3, false, (HP >> 4), 0>(z, 1, 0, tws, tid, NT); __syncthreads();
+        dif_pass<CSE_CORR_LOG2P, 3, false, (HP >> 7), 0>(z, 1, 0, tws, tid, NT); __syncthreads();
+#pragma unroll
+        for (int gi = 0; gi < 2; ++gi) {
+            const int grp = tid + gi * NT;
+            const real2* pz = z + SIDX(grp * 8);
+            real2 v[8];
+#pragma unroll
+            for (int m = 0; m < 8; ++m) v[m] = pz[m];
+            bfly8_dif<false, true>(v, mk2(R(1), R(0)), mk2(R(1), R(0)), mk2(R(1), R(0)));
+            const real2* __restrict__ q = Q + (size_t)pair * P + gi * 8 * NT + tid;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) acc[gi][m] = cadd(acc[gi][m], cmulc(q[m * NT], v[m]));
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int gi = 0; gi < 2; ++gi) {
+        const int grp = tid + gi * NT;
+        real2* pz = z + SIDX(grp * 8);
+        bfly8_dit<true, true>(acc[gi], mk2(R(1), R(0)), mk2(R(1), R(0)), mk2(R(1), R(0)));
+#pragma unroll
+        for (int m = 0; m < 8; ++m) pz[m] = acc[gi][m];
+    }
     __syncthreads();
-    fft_dit<CSE_CORR_LOG2P, true, -1>(z, 1, 0, tws, tid, NT, a.T->tw);
-    // first maximum over k = -maxlag .. maxlag
+    dit_pass<CSE_CORR_LOG2P, 3, true, 8, 0>(z, 1, 0, tws, tid, NT); __syncthreads();
+    dit_pass<CSE_CORR_LOG2P, 3, true, 64, 0>(z, 1, 0, tws, tid, NT); __syncthreads();
+    dit_pass<CSE_CORR_LOG2P, 3, true, 512, 0>(z, 1, 0, tws, tid, NT); __syncthreads();
+    // first maximum over k = -maxlag .. maxlag; output k + M of the last radix-2 stage is
+    // z[k + M] + z[k + M + P/2] conj(W_P^(k + M)), of which only the real part is needed
     const real invP = R(1) / (real)P;
     real best = -cse_inf();
     int bestk = 0x7fffffff;
     for (int k = -g.maxlag + tid; k <= g.maxlag; k += NT) {
-        const real c = z[SIDX(k + M)].x * invP - meanr * rsum[k + M];
+        const int i = k + M;
+        const real2 z0 = z[SIDX(i)], z1 = z[SIDX(i) + ZH], w = twg[i];
+        const real c = (z0.x + (z1.x * w.x + z1.y * w.y)) * invP - meanr * rsum[i];
         if (c > best) { best = c; bestk = k; }
     }
 #pragma unroll

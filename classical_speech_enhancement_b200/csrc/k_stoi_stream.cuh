@@ -63,6 +63,7 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
     // The run descriptor (first bin | length << 8 | band << 12 | runs of the band if first << 16) sits in shared memory.
     static_assert(T * 32 == NT, "one warp per frame of a batch");
     unsigned* run_s = koff_s + NK;                                            // 32
+    int* hb_s2 = reinterpret_cast<int*>(run_s + 32);                          // 2 x 64: this tile's (HBT + 1) rows of hbmap, double-buffered by tile parity
     if (tid < 32) {
         unsigned desc = 0;
         int r0 = 0;
@@ -90,11 +91,18 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
     int bad = 0, m_next = 0;
     const int na = (n10 + 4) / 5;
     for (int a0 = 0, t = 0; a0 < na; a0 += CSE_RS_A2, ++t) {
+        int* hb_s = hb_s2 + 64 * (t & 1);
         // ---- 1. input tile, SNR sums and finite check on the samples this tile owns
         {
             constexpr int TOT = 8 * (CSE_RS_A2 + 17), PERT = (TOT + NT - 1) / NT;
             static_assert(NT == 256 && H == 256 && PERT == 17, "tile-load index algebra below assumes 256 threads, 512 groups");
             const int j0 = 8 * a0 - 64;
+            if (tid < 3 * (HBT + 1)) {
+                const int row = HBT * t + tid / 3;
+                hb_s[tid] = row <= nhb ? hbmap[3 * HBT * t + tid] : -1;
+            }
+            if (tid >= 128 && j0 + TOT + (tid - 128) * (128 / (int)sizeof(real)) < L)      // next tile's lines start moving from DRAM to L2
+                cse_prefetch_l2(sig + j0 + TOT + (tid - 128) * (128 / (int)sizeof(real)));
             const bool interior = lag == 0 && j0 >= 0 && j0 + TOT <= L;      // uniform: no bounds, no shift
             real raw[PERT], cv[PERT];
             if (interior) {
@@ -163,9 +171,9 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
         // contribution (the second half of kept frame j-1) ASSIGNS, the other one ADDS; when both come
         // from one hop-block they are written together, otherwise the add runs after a barrier.
         for (int e = tid; e < YT; e += NT) {
-            const int hb = HBT * t + (e >> 7), n = e & 127;
+            const int hl = e >> 7, hb = HBT * t + hl, n = e & 127;
             if (hb < nhb) {
-                const int ja = hbmap[3 * hb], jb = hbmap[3 * hb + 1];
+                const int ja = hb_s[3 * hl], jb = hb_s[3 * hl + 1];
                 if (jb >= 0 && jb < K) {
                     const real y = yt[e];
                     real v = w_s[128 + n] * y;
@@ -176,9 +184,9 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
         }
         __syncthreads();
         for (int e = tid; e < YT; e += NT) {
-            const int hb = HBT * t + (e >> 7), n = e & 127;
+            const int hl = e >> 7, hb = HBT * t + hl, n = e & 127;
             if (hb < nhb) {
-                const int ja = hbmap[3 * hb], jb = hbmap[3 * hb + 1];
+                const int ja = hb_s[3 * hl], jb = hb_s[3 * hl + 1];
                 if (ja >= 0 && ja != jb) {                    // first half of kept frame ja completes block ja
                     const int slot = (ja & (RB - 1)) * 128 + n;
                     ring[slot] = r_fma(w_s[n], yt[e], ja > 0 ? ring[slot] : R(0));
@@ -188,7 +196,7 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
         __syncthreads();
         // ---- 4. transform every batch of T frames whose blocks are complete
         const int hb_end = HBT * (t + 1) < nhb ? HBT * (t + 1) : nhb;
-        const int jdone = hbmap[3 * hb_end + 2];              // kept frames with index < hb_end -> blocks B_0..B_{jdone-1} complete
+        const int jdone = hb_s[3 * (hb_end - HBT * t) + 2];              // kept frames with index < hb_end -> blocks B_0..B_{jdone-1} complete
         const bool last = a0 + CSE_RS_A2 >= na;
         while (m_next < Kf && (m_next + T <= jdone - 1 || last)) {
             const int m0 = m_next;
@@ -210,10 +218,12 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
                 const int run_lo = desc & 0xff, run_len = (desc >> 8) & 0xf, run_band = (desc >> 12) & 0xf, run_lead = desc >> 16;
                 const real2* zf = fbuf + wf * BST;
                 real* pwf = pw + wf * NK;
+                // chunks of 32 ALIGNED bins: the bit-reversed reads of a warp then differ only in their top
+                // five address bits, which the storage padding spreads over all banks
 #pragma unroll
-                for (int c = 0; c < (NK + 31) / 32; ++c) {
-                    const int i = lane + 32 * c;
-                    if (i < NK) {
+                for (int c = 0; c < (CSE_STOI_K1 + 31) / 32; ++c) {
+                    const int i = lane + 32 * c - CSE_STOI_K0;
+                    if (i >= 0 && i < NK) {
                         const unsigned off = koff_s[i];
                         const real2 z0 = zf[off & 0xffffu], z1 = zf[off >> 16];
                         const real2 E = mk2(R(0.5) * (z0.x + z1.x), R(0.5) * (z0.y - z1.y));
