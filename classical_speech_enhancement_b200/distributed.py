@@ -9,6 +9,8 @@ over NVLink on GPUs, gloo in the CPU tests).  The reference has no distributed c
 """
 import numpy as np
 
+from .engine import DEFAULT_CHUNK_ITEMS
+
 
 def shard_bounds(n_utts, world_size):
     """Contiguous, balanced blocks: rank r owns [b[r], b[r+1])."""
@@ -82,12 +84,12 @@ def gather_device_scores(engine, items, n_utts, device=None):
     return scores
 
 
-def sweep_sharded(clean, noisy, grids=None, select=True, chunk_items=4736, device=None, engine_kwargs=None):
+def sweep_sharded(clean, noisy, grids=None, select=True, chunk_items=DEFAULT_CHUNK_ITEMS, device=None, engine_kwargs=None):
     """Each rank sweeps its block of utterances; every rank returns the full gathered tables.
     ``clean`` / ``noisy`` are the full host arrays [U, L] (each rank slices its block)."""
     import torch.distributed as dist
     from . import sweep as sw
-    from .engine import SweepEngine
+    from .engine import DEFAULT_CHUNK_ITEMS, SweepEngine
     grids = grids or sw.DEFAULT_GRIDS
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0

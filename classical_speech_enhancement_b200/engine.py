@@ -20,6 +20,10 @@ from . import _lib
 from .grid import ALGORITHM_IDS, alg_eps, grid_points, plan
 
 SR = 16000
+# Candidates per launch: a common multiple of the resident CTAs of every hot kernel on 148 SMs (2, 3, 4 per SM ->
+# 296, 444, 592), so no launch ends in a partial wave; the candidate-waveform workspace is capped at 8 GiB.
+DEFAULT_CHUNK_ITEMS = 14208
+MAX_WAV_WORKSPACE_BYTES = 8 << 30
 
 #: runtime used when an engine is constructed without explicit lib/backend.  The product never
 #: changes it (-> libcse_sm100a.so + CUDA tensors); the CPU test-suite points it at the
@@ -87,7 +91,7 @@ class TorchCudaBackend:
 class SweepEngine:
     """One batch of ``U`` equal-length (clean, noisy) pairs resident on one device."""
 
-    def __init__(self, clean, noisy, sr=SR, lib=None, backend=None, chunk_items=4736, prepare_scoring=True):
+    def __init__(self, clean, noisy, sr=SR, lib=None, backend=None, chunk_items=DEFAULT_CHUNK_ITEMS, prepare_scoring=True):
         if sr != SR:
             raise ValueError("the sweep runs at 16 kHz (the reference resamples every pair to 16 kHz first)")
         self.lib = lib if lib is not None else (_runtime["lib"] or _lib.load())
@@ -100,7 +104,7 @@ class SweepEngine:
         if clean.shape != noisy.shape or clean.ndim != 2:
             raise ValueError("clean and noisy must both be [U, L]")
         self.U, self.L = clean.shape
-        self.chunk_items = int(chunk_items)
+        self.chunk_items = max(1, min(int(chunk_items), MAX_WAV_WORKSPACE_BYTES // max(1, self.L * np.dtype(self.real).itemsize)))
         be, lib_ = self.be, self.lib
         self.tables = be.empty((lib_.tables_bytes(),), np.uint8)
         lib_.tables_init(be.ptr(self.tables), be.stream())

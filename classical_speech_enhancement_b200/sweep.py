@@ -7,7 +7,7 @@ score tables (and, optionally, the reference's three winners per (utterance, alg
 """
 import numpy as np
 
-from .engine import SweepEngine
+from .engine import DEFAULT_CHUNK_ITEMS, SweepEngine
 from .grid import grid_points, select_best
 from .parameter_ranges import (param_ranges_mmse, param_ranges_omlsa, param_ranges_ss,
                                param_ranges_wiener)
@@ -75,7 +75,7 @@ def select_all(scores, points, pesq=None):
     return out
 
 
-def sweep_dataset(clean, noisy, grids=DEFAULT_GRIDS, sr=16000, select=True, chunk_items=4736, engine_kwargs=None):
+def sweep_dataset(clean, noisy, grids=DEFAULT_GRIDS, sr=16000, select=True, chunk_items=DEFAULT_CHUNK_ITEMS, engine_kwargs=None):
     """clean, noisy: host arrays [U, L] (equal-length, 16 kHz, pair-aligned).
 
     Returns ``{"scores", "points", "nominal", "unique", "selection", "engine"}``."""
@@ -86,7 +86,7 @@ def sweep_dataset(clean, noisy, grids=DEFAULT_GRIDS, sr=16000, select=True, chun
             "selection": select_all(scores, points) if select else None, "engine": eng}
 
 
-def sweep_pairs(pairs, grids=DEFAULT_GRIDS, sr=16000, select=True, chunk_items=4736, engine_kwargs=None):
+def sweep_pairs(pairs, grids=DEFAULT_GRIDS, sr=16000, select=True, chunk_items=DEFAULT_CHUNK_ITEMS, engine_kwargs=None):
     """Variable-length form of :func:`sweep_dataset`: ``pairs`` is a list of (clean, noisy) 1-D arrays
     (each pair equal length, pair-aligned, 16 kHz).  Pairs are bucketed by length - one engine (and
     one set of cached spectrograms) per distinct length - and results are returned in input order."""

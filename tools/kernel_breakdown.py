@@ -14,7 +14,7 @@ from classical_speech_enhancement_b200.engine import SweepEngine  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--utts", type=int, default=32)
-ap.add_argument("--chunk", type=int, default=4736)
+ap.add_argument("--chunk", type=int, default=14208)
 ap.add_argument("--length", type=int, default=48000)
 a = ap.parse_args()
 clean, noisy = make_shard(0, a.utts, a.length)

@@ -20,7 +20,7 @@ ap.add_argument("--hop", type=int, default=128)
 ap.add_argument("--method", default="min_tracking")
 ap.add_argument("--utts", type=int, default=16)
 ap.add_argument("--reps", type=int, default=3)
-ap.add_argument("--chunk", type=int, default=4736)
+ap.add_argument("--chunk", type=int, default=14208)
 ap.add_argument("--length", type=int, default=48000)
 a = ap.parse_args()
 ranges = dict(dict(sw.DEFAULT_GRIDS)[a.alg])
