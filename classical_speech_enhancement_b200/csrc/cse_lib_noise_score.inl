@@ -1,5 +1,5 @@
 // ------------------------------------------------------------------ K2 noise estimators
-static int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+static int next_pow2(int n) { int p = 32; while (p < n) p <<= 1; return p; }   // >= one element per lane of the sorting warp
 
 // (k, effective percentile) of Code/noise_estimation.py:29-41; short-signal rule :194-195,226-232
 static void quiet_rule(int nf, double percentile, int* k, double* pct, double* floor_rel) {

@@ -112,6 +112,7 @@ class SweepEngine:
         self.noisy = be.from_host(np.ascontiguousarray(noisy, dtype=self.real))
         self.h2d_bytes = 2 * clean.size * np.dtype(self.real).itemsize
         self._stft = {}
+        self._pow = {}
         self._noise = {}
         self._ws = {}
         self._plans = {}
@@ -186,12 +187,16 @@ class SweepEngine:
         return self._stft[key]
 
     def _power(self, n_fft, hop):
-        nf, nbp = self.n_frames(n_fft, hop), self.lib.bins_padded(n_fft)
-        P = self.be.empty((self.U, nf, nbp), self.real)
-        self.lib.stft_psd(self.be.ptr(self.tables), self.be.ptr(self.noisy), None, self.U, self.L, n_fft, hop, 0.0,
-                          None, self.be.ptr(P), self.be.stream())
-        self.launches += 1
-        return P
+        """|Y|^2 [U][nf][nbp] of the noisy signals, cached per shape (every estimator key of a shape reads it)."""
+        key = (n_fft, hop)
+        if key not in self._pow:
+            nf, nbp = self.n_frames(n_fft, hop), self.lib.bins_padded(n_fft)
+            P = self.be.empty((self.U, nf, nbp), self.real)
+            self.lib.stft_psd(self.be.ptr(self.tables), self.be.ptr(self.noisy), None, self.U, self.L, n_fft, hop, 0.0,
+                              None, self.be.ptr(P), self.be.stream())
+            self.launches += 1
+            self._pow[key] = P
+        return self._pow[key]
 
     def noise(self, key):
         """Noise PSD for key = (n_fft, hop, method, percentile|None, eps) -> (buffer, time_varying)."""
@@ -231,6 +236,7 @@ class SweepEngine:
 
     def drop_caches(self):
         self._stft.clear()
+        self._pow.clear()
         self._noise.clear()
 
     # ------------------------------------------------------------------ the sweep
