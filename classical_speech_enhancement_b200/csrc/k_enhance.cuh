@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
     constexpr int XST = C::XST;
     CSE_DYN_SMEM(smem_raw);
     real2* xs = reinterpret_cast<real2*>(smem_raw);                    // F * XST
-    real* ring = reinterpret_cast<real*>(xs + F * XST);                // W
+    real* ring = reinterpret_cast<real*>(xs + F * XST + 1);            // W (xs[F * XST] is a zero cell, see the gather plan)
     const int hop = a.hop;
     const int W = NFFT + (F - 1) * hop;
     real* wsteady = ring + W;                                          // hop: steady-state window sum-of-squares
@@ -201,6 +201,7 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
         pv_s[tid] = v;
     }
     for (int i = tid; i < W; i += NT) ring[i] = R(0);
+    if (tid == 0) xs[F * XST] = mk2(R(0), R(0));
     for (int m = tid; m < M; m += NT) w2s[m] = mk2(w[2 * m], w[2 * m + 1]);
     load_pass_twiddles<LOG2M, true>(tws, a.T->tw, tid, NT);
     for (int r = tid; r < hop; r += NT) {
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
     const int n_slots = is_pair ? PPT : (is_mid ? 1 : 0);
     GainState2 st[PPT];
     real nstat[PPT][2];
-    real2 twc[PPT];                                           // W_N^s of each pair slot
+    real2 twc[PPT];                                           // -i W_N^s of each pair slot
     real2 yv[PPT][2][F];
     real nv[PPT][2][F];
     // bins (ka, kb) of slot i: pair thread -> (s, M - s) with s = tid + i*NTB (slot 0: (0, M)); mid lane -> (M/2, -)
@@ -234,7 +235,8 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
         st[i].g_prev = mk2(R(1), R(1)); st[i].gam_prev = mk2(R(1), R(1)); st[i].nsm = mk2(R(0), R(0));
         nstat[i][0] = (!a.noise_tv && i < n_slots) ? Nu[bin_a(i)] : R(1);
         nstat[i][1] = (!a.noise_tv && is_pair) ? Nu[bin_b(i)] : R(1);
-        twc[i] = tw_load(a.T->tw, (is_pair ? tid + i * NTB : 0) * (CSE_TW_N / NFFT));
+        const real2 tws_i = tw_load(a.T->tw, (is_pair ? tid + i * NTB : 0) * (CSE_TW_N / NFFT));
+        twc[i] = mk2(tws_i.y, -tws_i.x);                      // -i W_N^s: conj-multiplying by it gives i D W_N^-s in one step
     }
     auto fetch = [&](int t0) {
         if (t0 + F <= nf) {
@@ -288,30 +290,46 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
 
     // Overlap-add gather plan.  Thread owns window pair-positions jj = tid + k*NT; frame f of an
     // iteration contributes its sample pair m = jj - f*hop/2 (if 0 <= m < M), which sits at a fixed
-    // shared-memory offset in the bit-reversed FFT output: all loop-invariant, computed once.
+    // shared-memory offset in the bit-reversed FFT output: all loop-invariant, computed once.  Per
+    // (k, thread) the contributing frames are listed first, as descriptors
+    //     byte offset of the FFT output in xs | byte offset of the window pair in w2s << 16,
+    // padded with "zero cell x w2s[0]" entries; the loop runs to the warp's largest count (for the
+    // usual hops every lane of a warp has the same count), so there is no per-element test.
     constexpr int KMAX = C::KMAX;
+    constexpr int KEMIT = 2;           // pairs tid, tid+NT: all emitted pairs when F*hop/2 <= 2*NT (hop <= n_fft/4 here); wider hops use the general path
     const int hh = hop >> 1;
     constexpr int F2 = (F + 1) / 2;
-    unsigned* zoff_s = reinterpret_cast<unsigned*>(tws + FftTwLayout<LOG2M, true>::SIZE);   // [KMAX * F2][NT], two 16-bit offsets each
+    static_assert((size_t)(F * XST + 1) * sizeof(real2) < 65536 && (size_t)M * sizeof(real2) < 65536, "16-bit byte offsets");
+    uint2* zoff_s = reinterpret_cast<uint2*>(tws + FftTwLayout<LOG2M, true>::SIZE);   // [KMAX * F2][NT]
+    static_assert(KMAX <= 8 && F <= 15, "gather counts are packed four bits per k");
+    unsigned gcount = 0;                                                              // warp-uniform entry count per k, 4 bits each
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
         const int jj = tid + k * NT;
+        unsigned d[2 * F2];
+        int n = 0;
 #pragma unroll
-        for (int f2 = 0; f2 < (F + 1) / 2; ++f2) {
-            unsigned packed = 0;
+        for (int f = 0; f < 2 * F2; ++f) d[f] = (unsigned)((F * XST) * sizeof(real2));           // zero cell, window pair 0
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int f = 2 * f2 + e, m = jj - f * hh;
-                const unsigned off = (f < F && jj < W / 2 && m >= 0 && m < M) ? (unsigned)(f * XST + SIDX(brev_n(m, LOG2M))) : 0xffffu;
-                packed |= off << (16 * e);
+        for (int f = 0; f < F; ++f) {
+            const int m = jj - f * hh;
+            if (jj < W / 2 && m >= 0 && m < M) {
+                const unsigned e = (unsigned)((f * XST + SIDX(brev_n(m, LOG2M))) * sizeof(real2)) | ((unsigned)(m * sizeof(real2)) << 16);
+#pragma unroll
+                for (int q = 0; q < F; ++q) if (q == n) d[q] = e;
+                ++n;
             }
-            zoff_s[(k * F2 + f2) * NT + tid] = packed;
         }
+#pragma unroll
+        for (int f2 = 0; f2 < F2; ++f2) zoff_s[(k * F2 + f2) * NT + tid] = make_uint2(d[2 * f2], d[2 * f2 + 1]);
+        unsigned nmax = (unsigned)n;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { const unsigned other = __shfl_xor_sync(0xffffffffu, nmax, o); nmax = other > nmax ? other : nmax; }
+        gcount |= nmax << (4 * k);
     }
 
     // Steady-state normalisation of the pairs this thread emits (window positions j < F*hop): the
     // window sum-of-squares only depends on j mod hop there, so 1/(N * wss) is loop-invariant.
-    constexpr int KEMIT = 2;           // pairs tid, tid+NT: all emitted pairs when F*hop/2 <= 2*NT (hop <= n_fft/4 here); wider hops use the general path
     real2* inv_ws_s = reinterpret_cast<real2*>(zoff_s + KMAX * F2 * NT);      // [KEMIT][NT]
 #pragma unroll
     for (int k = 0; k < KEMIT; ++k) {
@@ -345,11 +363,12 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
                         gain_pair<ALG>(yv[i][0][f], yv[i][1][f], mk2(nv[i][0][f], nv[i][1][f]), t == 0, st[i], pv, a.eps, smooth, xa, xb);
                         if (!is_pair) { xf[SIDX(M / 2)] = mk2(R(2) * xa.x, R(-2) * xa.y); continue; }   // 2 conj X[M/2]
                         if (s == 0) { xf[0] = mk2(xa.x + xb.x, xa.x - xb.x); continue; }                // DC, Nyquist (real)
-                        const real2 E = mk2(xa.x + xb.x, xa.y - xb.y);
-                        const real2 D = mk2(xa.x - xb.x, xa.y + xb.y);
-                        const real2 O = cmulc(D, twc[i]);                      // D * W_N^-s
-                        xf[SIDX(s)] = mk2(E.x - O.y, E.y + O.x);               // E + iO
-                        xf[SIDX(M - s)] = mk2(E.x + O.y, O.x - E.y);           // conj(E) + i conj(O)
+                        const real2 cb = mk2(xb.x, -xb.y);                     // conj X[M-s]
+                        const real2 E = cadd(xa, cb), D = csub(xa, cb);
+                        const real2 iO = cmulc(D, twc[i]);                     // i D W_N^-s (twc holds -i W_N^s)
+                        const real2 T = csub(E, iO);
+                        xf[SIDX(s)] = cadd(E, iO);                             // E + iO
+                        xf[SIDX(M - s)] = mk2(T.x, -T.y);                      // conj(E) + i conj(O) = conj(E - iO)
                     }
                 }
             }
@@ -373,15 +392,15 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
             if (slot >= W) slot -= W;
             real2 acc = *reinterpret_cast<real2*>(ring + slot);
             if (any) {                       // frames beyond n_frames were written as zero spectra
+                const int ng = (gcount >> (4 * k)) & 15;
+                const char* xsb = reinterpret_cast<const char*>(xs);
+                const char* wsb = reinterpret_cast<const char*>(w2s);
 #pragma unroll
                 for (int f2 = 0; f2 < F2; ++f2) {
-                    const unsigned packed = zoff_s[(k * F2 + f2) * NT + tid];   // own slots: no synchronisation needed
-#pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        const int f = 2 * f2 + e;
-                        const unsigned off = (packed >> (16 * e)) & 0xffffu;
-                        if (f < F && off != 0xffffu) acc = cfma2(xs[off], w2s[jj - f * hh], acc);
-                    }
+                    if (2 * f2 >= ng) break;
+                    const uint2 d = zoff_s[(k * F2 + f2) * NT + tid];   // own slots: no synchronisation needed
+                    acc = cfma2(*reinterpret_cast<const real2*>(xsb + (d.x & 0xffffu)), *reinterpret_cast<const real2*>(wsb + (d.x >> 16)), acc);
+                    acc = cfma2(*reinterpret_cast<const real2*>(xsb + (d.y & 0xffffu)), *reinterpret_cast<const real2*>(wsb + (d.y >> 16)), acc);
                 }
             }
             if (p < emit_end) {
