@@ -31,8 +31,12 @@
 // skipped at compile time.
 #ifdef CSE_EMU
 static const real c_rs[CSE_RS_ROWS * 8] = {CSE_RS_TAP_VALUES};
+static const real c_rs5[CSE_RS_ROWS * 5] = {CSE_RS_TAP_VALUES5};
 #else
 __device__ __constant__ real c_rs[CSE_RS_ROWS * 8] = {CSE_RS_TAP_VALUES};
+// five taps per row, unpadded: the packed FFMA2 form takes its taps from uniform registers, and 20 taps
+// of four rows arrive in five 16-byte uniform loads instead of eight
+__device__ __constant__ __align__(16) real c_rs5[CSE_RS_ROWS * 5] = {CSE_RS_TAP_VALUES5};
 #endif
 
 #define CSE_SR 16000

@@ -92,6 +92,7 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
     const int na = (n10 + 4) / 5;
     for (int a0 = 0, t = 0; a0 < na; a0 += CSE_RS_A2, ++t) {
         int* hb_s = hb_s2 + 64 * (t & 1);
+        int gap = 0;
         // ---- 1. input tile, SNR sums and finite check on the samples this tile owns
         {
             constexpr int TOT = 8 * (CSE_RS_A2 + 17), PERT = (TOT + NT - 1) / NT;
@@ -100,6 +101,10 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
             if (tid < 3 * (HBT + 1)) {
                 const int row = HBT * t + tid / 3;
                 hb_s[tid] = row <= nhb ? hbmap[3 * HBT * t + tid] : -1;
+            }
+            if (tid < HBT && HBT * t + tid < nhb) {            // does a kept frame start after a removed one in this tile?
+                const int ja = hbmap[3 * (HBT * t + tid)], jb = hbmap[3 * (HBT * t + tid) + 1];
+                gap = ja >= 0 && ja != jb;
             }
             if (tid >= 128 && j0 + TOT + (tid - 128) * (128 / (int)sizeof(real)) < L)      // next tile's lines start moving from DRAM to L2
                 cse_prefetch_l2(sig + j0 + TOT + (tid - 128) * (128 / (int)sizeof(real)));
@@ -142,7 +147,7 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
                 else if (k < PERT - 1 || jj < TOT) row[32 * (k - 8)].y = v;
             }
         }
-        __syncthreads();
+        const int anygap = __syncthreads_or(gap);
         if (!do_stoi) continue;                                                   // uniform: SNR only (the next tile load
                                                                                   // only overwrites what nobody reads)
         // ---- 2. resample into the shared tile: yt[5 (a - a0) + p]
@@ -159,7 +164,7 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
 #pragma unroll
                     for (int p = 0; p < 5; ++p) {
                         const int idx = 8 * p + 610 - 5 * jj;
-                        if (idx >= 0 && idx <= 580) acc[p] = cfma2(x, mk2(c_rs[jj * 8 + p], c_rs[jj * 8 + p]), acc[p]);
+                        if (idx >= 0 && idx <= 580) acc[p] = cfma2(x, mk2(c_rs5[jj * 5 + p], c_rs5[jj * 5 + p]), acc[p]);
                     }
                 }
 #pragma unroll
@@ -170,30 +175,35 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
         // ---- 3. fold the tile's hop-blocks into the overlap-added blocks B_j.  A block's first
         // contribution (the second half of kept frame j-1) ASSIGNS, the other one ADDS; when both come
         // from one hop-block they are written together, otherwise the add runs after a barrier.
-        for (int e = tid; e < YT; e += NT) {
-            const int hl = e >> 7, hb = HBT * t + hl, n = e & 127;
-            if (hb < nhb) {
+        {
+            static_assert(NT == 256 && HBT % 2 == 0, "each half of the CTA takes every other hop-block; a thread keeps one sample index n");
+            const int n = tid & 127, par = tid >> 7;
+            const real w0 = w_s[n], w1 = w_s[128 + n];
+#pragma unroll
+            for (int i = 0; i < HBT / 2; ++i) {
+                const int hl = 2 * i + par;
                 const int ja = hb_s[3 * hl], jb = hb_s[3 * hl + 1];
-                if (jb >= 0 && jb < K) {
-                    const real y = yt[e];
-                    real v = w_s[128 + n] * y;
-                    if (ja == jb) v = r_fma(w_s[n], y, v);    // consecutive kept frames share the hop-block
+                if (HBT * t + hl < nhb && jb >= 0 && jb < K) {
+                    const real y = yt[128 * hl + n];
+                    real v = w1 * y;
+                    if (ja == jb) v = r_fma(w0, y, v);        // consecutive kept frames share the hop-block
                     ring[(jb & (RB - 1)) * 128 + n] = v;
                 }
             }
-        }
-        __syncthreads();
-        for (int e = tid; e < YT; e += NT) {
-            const int hl = e >> 7, hb = HBT * t + hl, n = e & 127;
-            if (hb < nhb) {
-                const int ja = hb_s[3 * hl], jb = hb_s[3 * hl + 1];
-                if (ja >= 0 && ja != jb) {                    // first half of kept frame ja completes block ja
-                    const int slot = (ja & (RB - 1)) * 128 + n;
-                    ring[slot] = r_fma(w_s[n], yt[e], ja > 0 ? ring[slot] : R(0));
+            __syncthreads();
+            if (anygap) {                                     // uniform; rare: only where speech resumes after removed frames
+#pragma unroll
+                for (int i = 0; i < HBT / 2; ++i) {
+                    const int hl = 2 * i + par;
+                    const int ja = hb_s[3 * hl], jb = hb_s[3 * hl + 1];
+                    if (HBT * t + hl < nhb && ja >= 0 && ja != jb) {      // first half of kept frame ja completes block ja
+                        const int slot = (ja & (RB - 1)) * 128 + n;
+                        ring[slot] = r_fma(w0, yt[128 * hl + n], ja > 0 ? ring[slot] : R(0));
+                    }
                 }
+                __syncthreads();
             }
         }
-        __syncthreads();
         // ---- 4. transform every batch of T frames whose blocks are complete
         const int hb_end = HBT * (t + 1) < nhb ? HBT * (t + 1) : nhb;
         const int jdone = hb_s[3 * (hb_end - HBT * t) + 2];              // kept frames with index < hb_end -> blocks B_0..B_{jdone-1} complete

@@ -63,8 +63,9 @@ struct BlockCtx {
     std::vector<uint64_t> xch;      // 32 slots per warp
     unsigned char* smem;
     unsigned nthreads;
+    std::atomic<int> orflag[2];     // __syncthreads_or, alternating by call parity
 };
-struct Tls { BlockCtx* blk; unsigned lane, warp; };
+struct Tls { BlockCtx* blk; unsigned lane, warp, orphase; };
 extern thread_local Tls tls;
 }  // namespace cse_emu
 extern thread_local uint3 threadIdx, blockIdx;
@@ -77,6 +78,16 @@ thread_local dim3 blockDim, gridDim;
 #endif
 
 static inline void __syncthreads() { pthread_barrier_wait(&cse_emu::tls.blk->block_bar); }
+static inline int __syncthreads_or(int pred) {
+    cse_emu::Tls& t = cse_emu::tls;
+    std::atomic<int>& f = t.blk->orflag[t.orphase++ & 1];
+    if (pred) f.store(1);
+    pthread_barrier_wait(&t.blk->block_bar);
+    const int r = f.load();
+    pthread_barrier_wait(&t.blk->block_bar);
+    if (t.lane == 0 && t.warp == 0) f.store(0);     // next use of this flag is two calls (>= two barriers) away
+    return r;
+}
 static inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&cse_emu::tls.blk->warp_bar[cse_emu::tls.warp]); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
@@ -162,6 +173,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
         std::vector<std::thread> threads;
         for (unsigned long b = b0; b < b1; ++b) {
             BlockCtx* c = new BlockCtx;
+            c->orflag[0].store(0); c->orflag[1].store(0);
             c->nthreads = nthreads;
             pthread_barrier_init(&c->block_bar, nullptr, nthreads);
             c->warp_bar.resize(nwarps);
@@ -173,7 +185,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
             uint3 bi{(unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((unsigned long)grid.x * grid.y))};
             for (unsigned t = 0; t < nthreads; ++t) {
                 threads.emplace_back([=, &body]() {
-                    tls.blk = c; tls.lane = t % 32; tls.warp = t / 32;
+                    tls.blk = c; tls.lane = t % 32; tls.warp = t / 32; tls.orphase = 0;
                     threadIdx = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
                     blockIdx = bi; blockDim = block; gridDim = grid;
                     body();
