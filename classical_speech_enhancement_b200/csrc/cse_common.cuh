@@ -38,7 +38,9 @@ CSE_HD real2 mk2(real a, real b) { real2 r; r.x = a; r.y = b; return r; }
 #define CSE_PACKED_F32 1
 CSE_D real2 cadd(real2 a, real2 b) { return __fadd2_rn(a, b); }
 CSE_D real2 csub(real2 a, real2 b) { return __fadd2_rn(a, mk2(-b.x, -b.y)); }
-CSE_D real2 cmul(real2 a, real2 b) { return __ffma2_rn(mk2(-a.y, a.y), mk2(b.y, b.x), __fmul2_rn(mk2(a.x, a.x), b)); }
+// (the scalar halves of `a` are written as plain broadcasts: ptxas then uses the .F32 operand form and needs no register moves;
+// the swap and the per-half sign go on `b`, where they are operand modifiers)
+CSE_D real2 cmul(real2 a, real2 b) { return __ffma2_rn(mk2(a.y, a.y), mk2(-b.y, b.x), __fmul2_rn(mk2(a.x, a.x), b)); }
 CSE_D real2 cmulc(real2 a, real2 b) { /* a * conj(b) */ return __ffma2_rn(mk2(a.y, a.y), mk2(b.y, b.x), __fmul2_rn(mk2(a.x, a.x), mk2(b.x, -b.y))); }
 CSE_D real2 cscale(real2 a, real s) { return __fmul2_rn(a, mk2(s, s)); }
 CSE_D real2 cfma2(real2 a, real2 b, real2 c) { return __ffma2_rn(a, b, c); }      // elementwise a*b + c
