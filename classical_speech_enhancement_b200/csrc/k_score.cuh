@@ -177,7 +177,28 @@ __global__ void __launch_bounds__(512, 2) align_kernel(ScoreArgs a) {
     load_pass_twiddles<CSE_CORR_LOG2P, false>(tws, a.T->tw, tid, NT);
     double s = 0.0, e2 = 0.0;
     int bad = 0;
-    for (int i = tid; i < (CLEAN ? L : Nc); i += NT) {
+    int i_first = tid;
+#if !defined(CSE_FP64)
+    if (!CLEAN && (reinterpret_cast<size_t>(sig) & 15) == 0) {
+        // candidate side: 16-byte loads, eight samples summed in fp32 before they join the double
+        // accumulator (one conversion and one double add per eight samples; a non-finite sample makes
+        // its group sum non-finite, which is then examined sample by sample)
+        const float4* __restrict__ v4 = reinterpret_cast<const float4*>(sig);
+        const int n4 = Nc >> 2;
+        for (int g4 = tid; g4 < n4; g4 += 2 * NT) {
+            const float4 q1 = v4[g4];
+            const float4 q2 = g4 + NT < n4 ? v4[g4 + NT] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float gs = ((q1.x + q1.y) + (q1.z + q1.w)) + ((q2.x + q2.y) + (q2.z + q2.w));
+            s += (double)gs;
+            if (!r_finite(gs)) {
+                if (!r_finite(q1.x) || !r_finite(q1.y) || !r_finite(q1.z) || !r_finite(q1.w) ||
+                    !r_finite(q2.x) || !r_finite(q2.y) || !r_finite(q2.z) || !r_finite(q2.w)) bad = 1;
+            }
+        }
+        i_first = 4 * n4 + tid;
+    }
+#endif
+    for (int i = i_first; i < (CLEAN ? L : Nc); i += NT) {
         const real v = sig[i];
         if (i < Nc) { s += (double)v; if (!r_finite(v)) bad = 1; }
         if (CLEAN) e2 += (double)v * (double)v;
@@ -256,15 +277,28 @@ __global__ void __launch_bounds__(512, 2) align_kernel(ScoreArgs a) {
             const int pf = (b1 + 2) * B + tid * (128 / (int)sizeof(real));
             if (pf < Nc && pf < (b1 + 4) * B) cse_prefetch_l2(sig + pf);
         }
+        if (r1 >= B && r2 >= B) {                 // both blocks lie inside the window (uniform): no per-sample bounds
 #pragma unroll
-        for (int k = 0; k < HP / NT; ++k) {
-            const int i = tid + k * NT, ih = i + HP;
-            const real2 lo = mk2(i < r1 ? s1[i] : R(0), i < r2 ? s2[i] : R(0));            // i < HP < B
-            real2 hi = mk2(R(0), R(0));
-            if (k * NT < B - HP && ih < B) hi = mk2(ih < r1 ? s1[ih] : R(0), ih < r2 ? s2[ih] : R(0));
-            real2* pz = z + SIDX(i);
-            pz[0] = cadd(lo, hi);
-            pz[ZH] = cmul(csub(lo, hi), twg[i]);
+            for (int k = 0; k < HP / NT; ++k) {
+                const int i = tid + k * NT, ih = i + HP;
+                const real2 lo = mk2(s1[i], s2[i]);
+                real2 hi = mk2(R(0), R(0));
+                if (k * NT < B - HP && ih < B) hi = mk2(s1[ih], s2[ih]);
+                real2* pz = z + SIDX(i);
+                pz[0] = cadd(lo, hi);
+                pz[ZH] = cmul(csub(lo, hi), twg[i]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < HP / NT; ++k) {
+                const int i = tid + k * NT, ih = i + HP;
+                const real2 lo = mk2(i < r1 ? s1[i] : R(0), i < r2 ? s2[i] : R(0));            // i < HP < B
+                real2 hi = mk2(R(0), R(0));
+                if (k * NT < B - HP && ih < B) hi = mk2(ih < r1 ? s1[ih] : R(0), ih < r2 ? s2[ih] : R(0));
+                real2* pz = z + SIDX(i);
+                pz[0] = cadd(lo, hi);
+                pz[ZH] = cmul(csub(lo, hi), twg[i]);
+            }
         }
         __syncthreads();
         dif_pass<CSE_CORR_LOG2P, 3, false, (HP >> 1), 0>(z, 1, 0, tws, tid, NT); __syncthreads();

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
     real* ring = yt + YT;                                                     // RB * 128
     real* w_s = ring + RB * 128;                                              // 256
     real2* tws = reinterpret_cast<real2*>(w_s + 256);                         // 160
-    real2* ktw_s = tws + 160;                                                 // NK: W_512^k of the real-FFT split
+    real2* ktw_s = tws + 160;                                                 // NK: -i W_512^k of the real-FFT split
     unsigned* koff_s = reinterpret_cast<unsigned*>(ktw_s + NK);               // NK: storage offsets of bins k | 256-k
     real2* xs2 = fbuf;
     real* pw = yt;
@@ -55,7 +55,8 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
     load_pass_twiddles<8, true>(tws, a.T->tw, tid, NT);
     for (int i = tid; i < NK; i += NT) {
         const int k = CSE_STOI_K0 + i;
-        ktw_s[i] = tw_load(a.T->tw, k * (CSE_TW_N / 512));
+        const real2 wk = tw_load(a.T->tw, k * (CSE_TW_N / 512));
+        ktw_s[i] = mk2(wk.y, -wk.x);                                          // -i W_512^k
         koff_s[i] = (unsigned)SIDX(brev_n(k, 8)) | ((unsigned)SIDX(brev_n(256 - k, 8)) << 16);
     }
     // Band sums are done by one warp per frame: lane = a run of <= 9 consecutive bins inside one
@@ -210,15 +211,20 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
         const bool last = a0 + CSE_RS_A2 >= na;
         while (m_next < Kf && (m_next + T <= jdone - 1 || last)) {
             const int m0 = m_next;
-            for (int idx = tid; idx < T * 128; idx += NT) {
-                const int f = idx >> 7, mm = idx & 127, m = m0 + f;
-                const int j = mm < 64 ? m : m + 1, nn = (2 * mm) & 127, n = 2 * mm;
-                real2 v = mk2(R(0), R(0));
-                if (m < Kf) {
-                    const real* B = ring + (j & (RB - 1)) * 128;
-                    v = mk2(w_s[n] * B[nn], w_s[n + 1] * B[nn + 1]);
+            {
+                // thread = one packed sample pair mm of every other frame: window pair and block half are fixed
+                static_assert(NT == 256 && T == 8, "frame load: 128 pairs x 2 frame parities");
+                const int mm = tid & 127, par = tid >> 7;
+                const real2 wv = *reinterpret_cast<const real2*>(w_s + 2 * mm);
+                const int nn = (2 * mm) & 127, joff = mm < 64 ? 0 : 1;
+                real2* dst = fbuf + SIDX(mm);
+#pragma unroll
+                for (int i = 0; i < T / 2; ++i) {
+                    const int f = 2 * i + par, m = m0 + f;
+                    real2 v = mk2(R(0), R(0));
+                    if (m < Kf) v = cfma2(wv, *reinterpret_cast<const real2*>(ring + ((m + joff) & (RB - 1)) * 128 + nn), v);
+                    dst[f * BST] = v;                 // upper half of the zero-padded frame: never stored, the first pass knows
                 }
-                fbuf[f * BST + SIDX(mm)] = v;          // upper half of the zero-padded frame: never stored, the first pass knows
             }
             __syncthreads();
             fft_dif<8, false, 0, true>(fbuf, T, BST, tws, tid, NT);
@@ -235,11 +241,11 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
                     const int i = lane + 32 * c - CSE_STOI_K0;
                     if (i >= 0 && i < NK) {
                         const unsigned off = koff_s[i];
+                        // X[k] = (S + D (-i W^k)) / 2 with S = z0 + conj z1, D = z0 - conj z1; the 1/2 joins the square root
                         const real2 z0 = zf[off & 0xffffu], z1 = zf[off >> 16];
-                        const real2 E = mk2(R(0.5) * (z0.x + z1.x), R(0.5) * (z0.y - z1.y));
-                        const real2 O = mk2(R(0.5) * (z0.y + z1.y), R(-0.5) * (z0.x - z1.x));
-                        const real2 X = cadd(E, cmul(O, ktw_s[i]));
-                        pwf[i] = X.x * X.x + X.y * X.y;
+                        const real2 cz1 = mk2(z1.x, -z1.y);
+                        const real2 X = cadd(cadd(z0, cz1), cmul(csub(z0, cz1), ktw_s[i]));
+                        pwf[i] = r_fma(X.x, X.x, X.y * X.y);
                     }
                 }
                 __syncwarp();
@@ -252,7 +258,7 @@ __global__ void __launch_bounds__(256, 4) stoi_stream_kernel(ScoreArgs a) {
                     if (d < run_lead) sacc += o;
                 }
                 const int m = m0 + wf;
-                if (run_lead > 0 && m < Kf) ytob_g[run_band * Kf + m] = r_sqrt(sacc);
+                if (run_lead > 0 && m < Kf) ytob_g[run_band * Kf + m] = R(0.5) * r_sqrt(sacc);
             }
             __syncthreads();
             m_next += T;
