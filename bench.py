@@ -78,18 +78,22 @@ def grid_mean_bytes(L):
 
 # ------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  One poller (rank 0) covers
+    every GPU of the job; it is started before the warm-up so that its NVML start-up is over when the
+    timed region begins, and only the samples between mark() and stop() are used."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, indices):
+        self.indices, self.proc, self.lines, self.first = list(indices), None, [], 0
 
     def start(self):
+        if not self.indices:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", "--id=" + ",".join(str(i) for i in self.indices),
+                                          f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -100,14 +104,18 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        self.first = len(self.lines)
+
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi not sampled on this rank" if not self.indices else "nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        self.lines = self.lines[self.first:]
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
@@ -211,7 +219,7 @@ def workload_config(args, nominal_points, unique_points):
             "grid_points_unique": unique_points, "chunk_items": args.chunk,
             "cache_hygiene": "inputs larger than L2: waveforms + spectrogram / noise-PSD caches of the shard are "
                              "GBs and every step recomputes them from the raw signals; candidate waveforms are "
-                             "rewritten every chunk",
+                             "rewritten every chunk; score tables return through recycled pinned staging buffers",
             "parallelism": f"utterance-sharded x{args.gpus}"}
 
 
@@ -234,7 +242,8 @@ def main():
     import torch.distributed as dist
     from classical_speech_enhancement_b200 import sweep as sw
     from classical_speech_enhancement_b200.distributed import gather_device_scores, shard_bounds
-    from classical_speech_enhancement_b200.engine import SweepEngine
+    from classical_speech_enhancement_b200.engine import SweepEngine, reuse_result_buffers
+    reuse_result_buffers(True)      # each step's score tables are consumed (selection / checks) before the next step
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -270,11 +279,12 @@ def main():
         items = sw.run_engine_device(eng, u_pad=u_pad)
         return gather_device_scores(eng, items, args.utts, device=device)   # NCCL all_gather (N>1) + D2H + expansion
 
+    sampler = ClockSampler(range(world) if rank == 0 else [])
+    sampler.start()
     for _ in range(args.warmup):
         step_resident()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark()
     eng.enable_timing(True)
     launches0 = eng.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -76,7 +76,7 @@ def gather_device_scores(engine, items, n_utts, device=None):
             dist.all_gather_into_tensor(recv, send)
         else:
             dist.all_gather(list(recv.unbind(0)), send)
-        host = recv.cpu().numpy()
+        host = (engine.be.staged_to_host(recv) if recv.is_cuda and hasattr(engine.be, "staged_to_host") else recv.cpu().numpy().reshape(-1)).reshape(world, -1)
         if all(b[r + 1] - b[r] == b[1] - b[0] for r in range(world)):
             scores[name] = host.reshape(-1).view(engine.lib.score_dtype).reshape(n_utts, pl["n_points"])   # zero copy
         else:

@@ -28,13 +28,22 @@ MAX_WAV_WORKSPACE_BYTES = 8 << 30
 #: runtime used when an engine is constructed without explicit lib/backend.  The product never
 #: changes it (-> libcse_sm100a.so + CUDA tensors); the CPU test-suite points it at the
 #: thread-emulated build to exercise the host logic without a GPU.
-_runtime = {"lib": None, "backend_factory": None}
+_runtime = {"lib": None, "backend_factory": None, "reuse_result_buffers": False}
 _PLAN_CACHE = {}
+_PINNED_POOL = {}
 
 
-def configure_runtime(lib=None, backend_factory=None):
+def configure_runtime(lib=None, backend_factory=None, reuse_result_buffers=None):
     _runtime["lib"] = lib
     _runtime["backend_factory"] = backend_factory
+    if reuse_result_buffers is not None:
+        _runtime["reuse_result_buffers"] = bool(reuse_result_buffers)
+
+
+def reuse_result_buffers(on=True):
+    """Score tables of later sweeps may overwrite those of earlier ones (pinned staging buffers are recycled
+    per size): for pipelines that consume a step's tables before the next step.  Off by default."""
+    _runtime["reuse_result_buffers"] = bool(on)
 
 
 class TorchCudaBackend:
@@ -82,7 +91,23 @@ class TorchCudaBackend:
         return e
 
     def view_bytes_as(self, buf, dtype):
-        return buf.cpu().numpy().view(dtype)
+        return self.staged_to_host(buf).view(dtype)
+
+    def staged_to_host(self, buf):
+        """Device tensor -> numpy bytes.  With ``reuse_result_buffers`` (set by throughput drivers that consume
+        a step's tables before the next step) the copy lands in a process-wide pinned staging buffer of that
+        size, which the next copy of the same size overwrites; otherwise in a fresh pageable array."""
+        flat = buf.reshape(-1).view(self.torch.uint8)
+        if not _runtime.get("reuse_result_buffers"):
+            return flat.cpu().numpy()
+        key = (self.device.index, flat.numel())
+        host = _PINNED_POOL.get(key)
+        if host is None:
+            host = self.torch.empty((flat.numel(),), dtype=self.torch.uint8, pin_memory=True)
+            _PINNED_POOL[key] = host
+        host.copy_(flat, non_blocking=True)
+        self.torch.cuda.current_stream(self.device).synchronize()
+        return host.numpy()
 
     def slice_rows(self, buf, start, stop):
         return buf[start:stop]
@@ -286,7 +311,10 @@ class SweepEngine:
             Y = self.stft(n_fft, hop)
             N, tv = self.noise(key)
             n_rows = g["n_rows"]
-            params = be.from_host(g["params_host"])
+            pcache = pl.setdefault("params_dev", {})          # per engine: one upload per group, reused by later sweeps
+            params = pcache.get(id(g))
+            if params is None:
+                params = pcache[id(g)] = be.from_host(g["params_host"])
             keep.append(params)
             sc_ptr = be.ptr_at(uniq, self.U * g["col0"] * rec)          # group block [U][n_rows]
             total = self.U * n_rows

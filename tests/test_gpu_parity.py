@@ -291,3 +291,22 @@ def test_random_points_of_the_big_grids():
         for i in rng.choice(len(pts), 24, replace=False):
             ref = score_candidate(c, fn(n, 16000, **pts[i]), 16000)
             assert abs(sc[i]["stoi"] - ref["stoi"]) < TOL_STOI and abs(sc[i]["snr"] - ref["snr"]) < TOL_SNR_DB, (alg, pts[i])
+
+
+def test_recycled_pinned_result_buffers_give_the_same_tables():
+    """Throughput drivers may ask for score tables in recycled pinned staging buffers: same values, and the
+    next sweep of the same size overwrites the previous result (documented aliasing)."""
+    from classical_speech_enhancement_b200 import engine as eng_mod
+    clean, noisy = make_batch(2, 32000)
+    pts = grid.grid_points(dict(alpha=[0.9, 0.98], gain_floor=[0.05, 0.2], n_fft=[512], hop_length=[128],
+                           noise_percentile=[10.0], noise_method=["percentile", "min_tracking"]))
+    eng = engine_for(f32(clean), f32(noisy))
+    ref = eng.sweep("wiener", pts).copy()
+    eng_mod.reuse_result_buffers(True)
+    try:
+        a = eng.sweep("wiener", pts)
+        assert np.array_equal(a, ref)
+        b = eng.sweep("wiener", pts)
+        assert np.array_equal(b, ref) and np.shares_memory(a, b)
+    finally:
+        eng_mod.reuse_result_buffers(False)
