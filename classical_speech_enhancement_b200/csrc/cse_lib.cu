@@ -105,7 +105,7 @@ template <int ALG, int LOG2N>
 static int launch_enhance(const EnhanceArgs& a, int n_items, void* stream) {
     typedef EnhanceCfg<LOG2N> C;
     const int W = C::NFFT + (C::F - 1) * a.hop;
-    const size_t smem = (size_t)(C::F * C::XST + 1) * sizeof(real2) + (size_t)(W + a.hop + 8) * sizeof(real) + (size_t)(C::M + FftTwLayout<LOG2N - 1, true>::SIZE) * sizeof(real2) +
+    const size_t smem = (size_t)(C::F * C::XST + 1) * sizeof(real2) + (size_t)(W + a.hop + 16) * sizeof(real) + (size_t)(C::M + FftTwLayout<LOG2N - 1, true>::SIZE) * sizeof(real2) +
                         (size_t)C::KMAX * ((C::F + 1) / 2) * C::NT * 2 * sizeof(unsigned) + (size_t)2 * C::NT * sizeof(real2);
     auto kfn = enhance_kernel<ALG, LOG2N>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

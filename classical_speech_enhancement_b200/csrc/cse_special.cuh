@@ -97,18 +97,17 @@ CSE_D real2 cse_mmse_bessel_term2(real2 v) {
     CSE_POLY_DECL(M_LO);
     CSE_POLY_DECL(M_HI);
     const real2 lo = poly2(c_M_LO, p_fma(v, p_set(R(0.125)), p_set(R(-1))));
-    const real2 vv = p_max(v, p_set(R(16)));                        // keep the high branch's argument in range
-    const real2 hi = p_mul(poly2(c_M_HI, p_fma(p_rcp(vv), p_set(R(40)), p_set(R(-1.5)))), p_sqrt(vv));
+    const real2 hi = p_mul(poly2(c_M_HI, p_fma(p_rcp(v), p_set(R(40)), p_set(R(-1.5)))), p_sqrt(v));   // discarded below 16 (v >= eps > 0)
     return mk2(v.x <= R(16) ? lo.x : hi.x, v.y <= R(16) ? lo.y : hi.y);
 }
 // enegv = exp(-v) (shared with the speech-presence probability of the caller)
 CSE_D real2 cse_half_e1_log2_2(real2 v, real2 enegv) {
     CSE_POLY_DECL(E_LO);
     CSE_POLY_DECL(E_HI);
-    const real2 vl = p_min(v, p_set(R(1)));                         // each branch evaluated inside its own range
-    const real2 lo = p_mul(p_set(R(0.5)), p_sub(p_mul(p_set(CSE_LOG2E), poly2(c_E_LO, p_fma(vl, p_set(R(2)), p_set(R(-1))))), p_log2(vl)));
-    const real2 vh = p_max(v, p_set(R(1)));
-    const real2 rv = p_rcp(vh);
+    // both branches are evaluated on v itself: outside its range a branch only produces a value (possibly inf / NaN)
+    // that the per-lane select below discards, so no clamping is needed (v is already clipped to [1e-12, v_max])
+    const real2 lo = p_mul(p_set(R(0.5)), p_sub(p_mul(p_set(CSE_LOG2E), poly2(c_E_LO, p_fma(v, p_set(R(2)), p_set(R(-1))))), p_log2(v)));
+    const real2 rv = p_rcp(v);
     const real2 t = p_mul(p_fma(rv, p_set(R(2)), p_set(R(-1.0125))), p_set(R(1.0 / 0.9875)));
     const real2 hi = p_mul(p_mul(p_set(R(0.5) * CSE_LOG2E), poly2(c_E_HI, t)), p_mul(enegv, rv));
     return mk2(v.x <= R(1) ? lo.x : hi.x, v.y <= R(1) ? lo.y : hi.y);

@@ -83,8 +83,8 @@ struct GainState2 { real2 g_prev, gam_prev, nsm; };
 template <int ALG>
 CSE_D void gain_pair(real2 Ya, real2 Yb, real2 Nraw, bool first, GainState2& st, const real* __restrict__ pv,
                      real eps, bool smooth, real2& Sa, real2& Sb) {
-    const real2 re = mk2(Ya.x, Yb.x), im = mk2(Ya.y, Yb.y);
-    const real2 Pw = p_fma(re, re, p_mul(im, im));
+    // |Y|^2 of the two bins with scalar FMAs: gathering (re, re') and (im, im') pairs for a packed form costs eight moves
+    const real2 Pw = mk2(r_fma(Ya.x, Ya.x, Ya.y * Ya.y), r_fma(Yb.x, Yb.x, Yb.y * Yb.y));
     real2 Nt = p_max(Nraw, p_set(eps));
     if (ALG == 0) {
         const real2 Pc = p_max(p_fma(p_set(-pv[0]), Nt, Pw), p_mul(p_set(pv[1]), Nt));
@@ -94,13 +94,13 @@ CSE_D void gain_pair(real2 Ya, real2 Yb, real2 Nraw, bool first, GainState2& st,
             const real pw = e ? Pw.y : Pw.x, pc = e ? Pc.y : Pc.x;
             g[e] = pw > R(1e-30) ? r_fsqrt(pc * r_rcp(pw)) : (pw > R(0) ? r_sqrt(pc) / r_sqrt(pw) : R(-1));
         }
-        Sa = g[0] >= R(0) ? mk2(Ya.x * g[0], Ya.y * g[0]) : mk2(r_sqrt(Pc.x), R(0));
-        Sb = g[1] >= R(0) ? mk2(Yb.x * g[1], Yb.y * g[1]) : mk2(r_sqrt(Pc.y), R(0));
+        Sa = g[0] >= R(0) ? cscale(Ya, g[0]) : mk2(r_sqrt(Pc.x), R(0));
+        Sb = g[1] >= R(0) ? cscale(Yb, g[1]) : mk2(r_sqrt(Pc.y), R(0));
         return;
     }
     if (ALG >= 2 && smooth) {
         const real mu = (ALG == 2) ? pv[4] : pv[3];
-        if (!first) Nt = p_fma(p_set(mu), st.nsm, p_mul(p_set(R(1) - mu), Nt));
+        if (!first) Nt = p_fma(p_set(mu), st.nsm, p_mul(p_set(pv[9]), Nt));
         st.nsm = Nt;
         Nt = p_max(Nt, p_set(eps));
     }
@@ -108,7 +108,7 @@ CSE_D void gain_pair(real2 Ya, real2 Yb, real2 Nraw, bool first, GainState2& st,
     const real2 gm1 = p_add(gam, p_set(R(-1)));
     const real2 direct = p_max(gm1, p_set(R(0)));
     const real alpha = pv[0];
-    const real2 rec = p_fma(p_set(alpha), p_mul(p_mul(st.g_prev, st.g_prev), st.gam_prev), p_mul(p_set(R(1) - alpha), direct));
+    const real2 rec = p_fma(p_set(alpha), p_mul(p_mul(st.g_prev, st.g_prev), st.gam_prev), p_mul(p_set(pv[8]), direct));
     real2 G;
     if (ALG == 1) {
         const real2 xi = p_max(first ? direct : rec, p_set(R(1e-10)));
@@ -129,14 +129,14 @@ CSE_D void gain_pair(real2 Ya, real2 Yb, real2 Nraw, bool first, GainState2& st,
             // p = 1 / (1 + (1-q) / (q Lambda + eps)), Lambda = exp(v)/(1+xi); numerator and denominator
             // multiplied by exp(-v) so that one exponential serves both E1 and the presence probability
             const real2 A = p_fma(p_set(eps), enegv, p_mul(p_set(q), r));
-            const real2 p = p_clip(p_mul(A, p_rcp(p_fma(p_set(R(1) - q), enegv, A))), R(0), R(1));
+            const real2 p = p_clip(p_mul(A, p_rcp(p_fma(p_set(pv[10]), enegv, A))), R(0), R(1));
             G = p_clip(p_exp2(p_fma(p, p_add(lg2, p_set(-lg2gf)), p_set(lg2gf))), gf, R(1));
         }
     }
     st.g_prev = G;
     st.gam_prev = gam;
-    Sa = mk2(Ya.x * G.x, Ya.y * G.x);
-    Sb = mk2(Yb.x * G.y, Yb.y * G.y);
+    Sa = cscale(Ya, G.x);
+    Sb = cscale(Yb, G.y);
 }
 
 struct EnhanceArgs {
@@ -183,8 +183,8 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
     const int hop = a.hop;
     const int W = NFFT + (F - 1) * hop;
     real* wsteady = ring + W;                                          // hop: steady-state window sum-of-squares
-    real* pv_s = wsteady + hop;                                        // 8 params
-    real2* w2s = reinterpret_cast<real2*>(pv_s + 8);                   // M window pairs (w[2m], w[2m+1])
+    real* pv_s = wsteady + hop;                                        // 8 params + derived constants (16 slots)
+    real2* w2s = reinterpret_cast<real2*>(pv_s + 16);                   // M window pairs (w[2m], w[2m+1])
     real2* tws = w2s + M;                                              // per-pass twiddles of the half-size FFT (FftTwLayout)
     const int tid = threadIdx.x;
     const int item = a.item0 + blockIdx.x;
@@ -210,7 +210,12 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
         wsteady[r] = s;
     }
     __syncthreads();
-    if (ALG == 3 && tid == 0) pv_s[6] = r_log(pv_s[2]) * CSE_LOG2E;     // log2(gain_floor)
+    if (tid == 0) {
+        if (ALG == 3) pv_s[6] = r_log(pv_s[2]) * CSE_LOG2E;             // log2(gain_floor)
+        pv_s[8] = R(1) - pv_s[0];                                       // 1 - alpha
+        pv_s[9] = R(1) - ((ALG == 2) ? pv_s[4] : pv_s[3]);              // 1 - noise_mu
+        pv_s[10] = R(1) - pv_s[4];                                      // 1 - q (Log-MMSE)
+    }
     __syncthreads();
     const real* pv = pv_s;                   // parameters stay in shared memory (broadcast reads) to save registers
     const real mu_raw = (ALG == 2) ? (real)a.params[c].v[4] : (ALG == 3) ? (real)a.params[c].v[3] : R(-1);
