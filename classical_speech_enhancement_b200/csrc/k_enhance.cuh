@@ -153,6 +153,9 @@ struct EnhanceArgs {
 #ifndef CSE_ENH_MB_SMALL
 #define CSE_ENH_MB_SMALL 4    // resident CTAs per SM asked of ptxas for the <= 200-thread variants (n_fft <= 512)
 #endif
+#ifndef CSE_ENH_MB_LARGE
+#define CSE_ENH_MB_LARGE 3    // same for the 288-thread variants (n_fft >= 1024): 72 registers; 2 (104 registers, no spills) measured slower
+#endif
 #ifndef CSE_ENH_CAP
 #define CSE_ENH_CAP 256
 #endif
@@ -209,7 +212,7 @@ CSE_D void emit_edge_pair(real2 acc, int p, int i, int L, int nf, int hop, int h
 // so it is formed in registers and written straight into the FFT buffer - no separate split
 // pass, no exchange through shared memory.
 template <int ALG, int LOG2N>
-__global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT > 200 ? 3 : CSE_ENH_MB_SMALL)) enhance_kernel(EnhanceArgs a) {
+__global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT > 200 ? CSE_ENH_MB_LARGE : CSE_ENH_MB_SMALL)) enhance_kernel(EnhanceArgs a) {
     typedef EnhanceCfg<LOG2N> C;
     constexpr int NFFT = C::NFFT, M = C::M, LOG2M = LOG2N - 1, NTB = C::NTB, PPT = C::PPT, NT = C::NT, F = C::F;
     constexpr int XST = C::XST;
