@@ -9,8 +9,9 @@
 // and librosa.istft(S, hop_length, win_length=n_fft, window="hann", center=True, length=L).
 //
 // The decision-directed recursion is sequential over frames but independent per bin, so each
-// thread carries (previous gain, previous a-posteriori SNR, smoothed noise PSD) for its BPT bins
-// in registers and marches F frames per iteration.  The F gained spectra are turned into F packed
+// thread carries (previous gain, previous a-posteriori SNR, smoothed noise PSD) for its bin pairs
+// in registers (both bins of a pair as the two halves of packed FP32 instructions) and marches F
+// frames per iteration.  The F gained spectra are turned into F packed
 // half-size inverse FFTs in shared memory (F is chosen so that every thread has a radix-8
 // butterfly per pass), windowed, overlap-added into a ring buffer, normalised by the window
 // sum-of-squares and streamed out, F*hop finished samples per iteration.
@@ -18,9 +19,9 @@
 // Thread layout: NTB = min(n_fft/4, 256) "pair" threads own the bin pairs (s, M-s), M = n_fft/2
 // (slot 0 is DC + Nyquist); one extra warp carries the self-paired bin M/2 in its lane 0 so that
 // no thread does extra work in front of the barrier; all NTB+32 threads share the FFT /
-// overlap-add loops.  Y / N reads (coalesced, issued
-// for the NEXT iteration right after the gain phase so they fly during the FFT) and waveform
-// writes are coalesced.  Round-1 profile and the changes it drove: profiles/r01_*.md.
+// overlap-add loops.  Y / N reads (coalesced, issued for the NEXT iteration right after the FFT
+// so that they fly during the overlap-add) and waveform writes are coalesced.  Round-1 profiles and
+// the changes they drove: profiles/r01*_ncu.md, DESIGN.md section 8.
 #pragma once
 #include "cse_fft.cuh"
 #include "cse_special.cuh"

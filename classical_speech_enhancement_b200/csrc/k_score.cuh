@@ -14,8 +14,9 @@
 // packed the same way, accumulated over block pairs in registers and inverse-transformed once:
 //   Re IFFT( sum_pairs Q_pair * conj(Z_pair) )[k + 1600] = sum_n clean0[n + k] * sig[n].
 // The forward transforms are DIF (bit-reversed output), the inverse is DIT (bit-reversed
-// input), so no reordering pass exists and the cached clean spectra are simply stored in DIF
-// order.  Mean removal of the candidate is applied afterwards (correlation is linear).
+// input), so no reordering pass exists; the cached clean spectra are stored in the order in which
+// the candidate kernel's last forward pass consumes them (see align_kernel).  Mean removal of the
+// candidate is applied afterwards (correlation is linear).
 //
 // STOI: polyphase 16k->10k resampling through a de-interleaved shared-memory tile, frames
 // gathered through the clean signal's VAD list (cached per utterance), 512-point real FFTs as
@@ -26,7 +27,8 @@
 #include "cse_resampler_taps.h"
 
 // Resampler taps as compile-time-indexed constant-bank operands: with the row loop fully
-// unrolled every tap is a c[bank][offset] operand of its FFMA (no load instruction), and the
+// unrolled every tap is a c[bank][offset] operand of its FFMA (scalar form) or arrives through a
+// uniform register (packed FFMA2 form of the candidate kernel), and the
 // structurally zero taps (each output phase only reaches 116-117 of the 136 tile rows) are
 // skipped at compile time.
 #ifdef CSE_EMU
