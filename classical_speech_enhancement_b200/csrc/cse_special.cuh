@@ -62,25 +62,6 @@ template <int N> CSE_HD real horner(const real (&a)[N], real t) {
 #define CSE_POLY_DECL(name) const real c_##name[CSE_##name##_F32_N] = CSE_##name##_F32_POLY
 #endif
 
-CSE_D real cse_mmse_bessel_term_fast(real v) {
-    if (v <= R(16)) {
-        CSE_POLY_DECL(M_LO);
-        return CSE_POLY_EVAL(M_LO, v * R(0.125) - R(1));
-    }
-    CSE_POLY_DECL(M_HI);
-    return CSE_POLY_EVAL(M_HI, R(40) * r_rcp(v) - R(1.5)) * r_fsqrt(v);
-}
-// E1(v) * 0.5 * log2(e): the Log-MMSE gain is evaluated in the log2 domain
-CSE_D real cse_half_e1_log2_fast(real v) {
-    if (v <= R(1)) {
-        CSE_POLY_DECL(E_LO);
-        return R(0.5) * (CSE_LOG2E * CSE_POLY_EVAL(E_LO, v + v - R(1)) - r_flog2(v));    // ln v = log2 v * ln 2
-    }
-    CSE_POLY_DECL(E_HI);
-    const real rv = r_rcp(v);
-    return (R(0.5) * CSE_LOG2E) * CSE_POLY_EVAL(E_HI, (rv + rv - R(1.0125)) * R(1.0 / 0.9875)) * r_fexp2(-v * CSE_LOG2E) * rv;
-}
-
 // ---- two-lane forms (both range branches evaluated for both lanes, selected per lane) ----
 template <int N> CSE_D real2 horner2(const real (&a)[N], real2 t) {
     real2 r = p_set(a[N - 1]);

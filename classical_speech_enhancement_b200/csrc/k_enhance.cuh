@@ -26,59 +26,9 @@
 #include "cse_fft.cuh"
 #include "cse_special.cuh"
 
-struct GainState { real g_prev, gam_prev, nsm; };
-
-template <int ALG>
-CSE_D real2 gain_apply(real2 Yv, real Nraw, bool first, GainState& st, const real* __restrict__ pv,
-                       real eps, bool smooth) {
-    const real Pw = r_fma(Yv.x, Yv.x, Yv.y * Yv.y);
-    real Nt = r_max(Nraw, eps);
-    if (ALG == 0) {
-        // Pc = max(P - alpha N, beta N); S = sqrt(Pc) * exp(j angle(Y)) = Y * sqrt(Pc / P)
-        const real Pc = r_max(r_fma(-pv[0], Nt, Pw), pv[1] * Nt);
-        if (Pw > R(1e-30)) { const real g = r_fsqrt(Pc * r_rcp(Pw)); return mk2(Yv.x * g, Yv.y * g); }
-        if (Pw > R(0)) { const real g = r_sqrt(Pc) / r_sqrt(Pw); return mk2(Yv.x * g, Yv.y * g); }
-        return mk2(r_sqrt(Pc), R(0));
-    }
-    if (ALG >= 2 && smooth) {           // recursive smoothing of a time-varying noise PSD
-        const real mu = (ALG == 2) ? pv[4] : pv[3];
-        Nt = first ? Nt : r_fma(mu, st.nsm, (R(1) - mu) * Nt);
-        st.nsm = Nt;
-        Nt = r_max(Nt, eps);
-    }
-    const real gam = r_max(Pw * r_rcp(Nt), eps);
-    const real direct = r_max(gam - R(1), R(0));
-    const real alpha = pv[0];
-    const real rec = r_fma(alpha, st.g_prev * st.g_prev * st.gam_prev, (R(1) - alpha) * direct);
-    real G;
-    if (ALG == 1) {
-        const real xi = r_max(first ? direct : rec, R(1e-10));
-        G = r_clip(xi * r_rcp(R(1) + xi), pv[1], R(1));
-    } else {
-        const real xi = r_max(first ? (gam - R(1)) : rec, pv[1]);
-        const real r = r_rcp(R(1) + xi);
-        const real xr = xi * r;                                   // xi / (1 + xi)
-        if (ALG == 2) {
-            const real v = r_clip(xr * gam, eps, R(80));
-            const real A = R(0.88622692545275801365) * r_fsqrt(v) * r_rcp(gam + eps);
-            G = r_clip(A * cse_mmse_bessel_term_fast(v), pv[2], pv[3]);
-        } else {
-            const real gf = pv[2], q = pv[4], vmax = pv[5], lg2gf = pv[6];
-            const real v = r_clip(xr * gam, R(1e-12), vmax);
-            const real lg2 = r_flog2(xr) + cse_half_e1_log2_fast(v);            // log2(G_lsa)
-            const real ql = r_fma(q, r_fexp2(v * CSE_LOG2E) * r, eps);          // q * Lambda + eps
-            const real p = r_clip(ql * r_rcp(ql + (R(1) - q)), R(0), R(1));     // 1 / (1 + (1-q)/ql)
-            G = r_clip(r_fexp2(r_fma(p, lg2 - lg2gf, lg2gf)), gf, R(1));        // G_lsa^p gf^(1-p)
-        }
-    }
-    st.g_prev = G;
-    st.gam_prev = gam;
-    return mk2(Yv.x * G, Yv.y * G);
-}
-
-// Two bins at once (the thread's pair (s, M-s)): lane .x = bin a, lane .y = bin b.  Same
-// arithmetic as gain_apply, with every FP add / mul / fma issued as one packed instruction for
-// both bins.  State is packed the same way.
+// The gain rule for two bins at once (the thread's pair (s, M-s)): lane .x = bin a, lane .y = bin b,
+// every FP add / mul / fma issued as one packed instruction for both bins; the decision-directed
+// state (previous gain, previous a-posteriori SNR, smoothed noise PSD) is packed the same way.
 struct GainState2 { real2 g_prev, gam_prev, nsm; };
 
 template <int ALG>
