@@ -26,18 +26,15 @@
 #include "cse_fft.cuh"
 #include "cse_resampler_taps.h"
 
-// Resampler taps as compile-time-indexed constant-bank operands: with the row loop fully
-// unrolled every tap is a c[bank][offset] operand of its FFMA (scalar form) or arrives through a
-// uniform register (packed FFMA2 form of the candidate kernel), and the
+// Resampler taps of the candidate kernel as compile-time-indexed constant-bank values: with the row
+// loop fully unrolled every tap arrives through a uniform register of its packed FFMA2, and the
 // structurally zero taps (each output phase only reaches 116-117 of the 136 tile rows) are
 // skipped at compile time.
 #ifdef CSE_EMU
-static const real c_rs[CSE_RS_ROWS * 8] = {CSE_RS_TAP_VALUES};
 static const real c_rs5[CSE_RS_ROWS * 5] = {CSE_RS_TAP_VALUES5};
 #else
-__device__ __constant__ real c_rs[CSE_RS_ROWS * 8] = {CSE_RS_TAP_VALUES};
 // five taps per row, unpadded: the packed FFMA2 form takes its taps from uniform registers, and 20 taps
-// of four rows arrive in five 16-byte uniform loads instead of eight
+// of four rows arrive in five 16-byte uniform loads
 __device__ __constant__ __align__(16) real c_rs5[CSE_RS_ROWS * 5] = {CSE_RS_TAP_VALUES5};
 #endif
 
@@ -364,10 +361,10 @@ __global__ void __launch_bounds__(512, 2) align_kernel(ScoreArgs a) {
 }
 
 // ---------------------------------------------------------------- resampler
-// One pass: outputs y10[5a + p], a in [a0, a0 + A), from the de-interleaved tile xs[c][ap]
-// (c = sample index mod 8, AP = A + 17 columns).  TA = accumulator type.  CONSTTAPS: taps from
-// the constant bank (candidate path); otherwise from the table G (double-precision clean path).
-template <class TA, class TG, class TO, bool CONSTTAPS>
+// One pass of the clean-side (double precision) resampler: outputs y10[5a + p], a in [a0, a0 + A), from
+// the de-interleaved tile xs[c][ap] (c = sample index mod 8, AP = A + 17 columns), taps from the table G.
+// The candidate side has its own packed form in k_stoi_stream.cuh.
+template <class TA, class TG, class TO>
 CSE_D void resample_pass(const real* __restrict__ sig, int L, int lag, bool finalize, const TG* __restrict__ G /*[136][8]*/,
                          TA* xs, int a0, TO* __restrict__ y10, int n10, int tid, int nth,
                          const unsigned char* __restrict__ need = nullptr) {
@@ -379,17 +376,7 @@ CSE_D void resample_pass(const real* __restrict__ sig, int L, int lag, bool fina
         const int a = a0 + al;
         if (5 * a < n10 && (need == nullptr || need[a])) {
             TA acc[5] = {0, 0, 0, 0, 0};
-            if (CONSTTAPS) {
-#pragma unroll
-                for (int jj = 6; jj <= 128; ++jj) {                 // rows 0-5 and 129-135 hold no tap
-                    const TA x = xs[(jj & 7) * AP + al + (jj >> 3)];
-#pragma unroll
-                    for (int p = 0; p < 5; ++p) {
-                        const int idx = 8 * p + 610 - 5 * jj;        // compile-time after unrolling
-                        if (idx >= 0 && idx <= 580) acc[p] += x * (TA)c_rs[jj * 8 + p];
-                    }
-                }
-            } else {
+            {
                 for (int o = 0; o < 17; ++o) {
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
@@ -424,7 +411,7 @@ __global__ void __launch_bounds__(256) clean_vad_kernel(ScoreArgs a, double* __r
     int* kept = reinterpret_cast<int*>(rec + g.off_kept);
     const int na = (g.n10 + 4) / 5;
     for (int a0 = 0; a0 < na; a0 += CSE_RS_A)
-        resample_pass<double, double, double, false>(sig, g.L, 0, false, &a.T->rs_d[0][0], xs, a0, yd, g.n10, tid, 256);
+        resample_pass<double, double, double>(sig, g.L, 0, false, &a.T->rs_d[0][0], xs, a0, yd, g.n10, tid, 256);
     __threadfence_block();
     __syncthreads();
     // frame energies in dB: 20 log10(||w * frame|| + EPS)
