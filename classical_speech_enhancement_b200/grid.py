@@ -108,3 +108,41 @@ def select_best(points, stoi, pesq, snr, valid):
                 best[c] = {"index": i, "score": vals[c], "params": dict(points[i]),
                            "stoi": stoi[i], "pesq": pesq[i], "snr": snr[i]}
     return best
+
+
+def select_best_batch(points, stoi, pesq, snr, valid):
+    """``select_best`` for U utterances at once: the scan is sequential over the grid (hysteresis makes
+    it order-dependent) but independent per utterance, so every step is one vector operation over the
+    utterances.  ``stoi``, ``snr``: float arrays [U, P]; ``valid``: bool [U, P]; ``pesq``: float array
+    [U, P] with NaN where the reference's ``calculate_pesq`` returned None (candidate skipped), or None
+    for "PESQ = 0.0 everywhere".  Returns a list of U dicts identical to ``select_best``'s."""
+    import numpy as np
+    stoi = np.asarray(stoi, dtype=np.float64)
+    snr = np.asarray(snr, dtype=np.float64)
+    U, P = stoi.shape
+    pq = np.zeros((U, P)) if pesq is None else np.asarray(pesq, dtype=np.float64)
+    ok = np.asarray(valid, dtype=bool) & ~np.isnan(pq)
+    vals = {"stoi": stoi, "pesq": pq, "balance": 0.5 * stoi + 0.5 * (np.maximum(0, pq) / 4.5)}
+    best_score = {c: np.full(U, -1.0) for c in TOL}
+    best_index = {c: np.full(U, -1, dtype=np.int64) for c in TOL}
+    for i in range(P):
+        oki = ok[:, i]
+        if not oki.any():
+            continue
+        for c in TOL:
+            upd = oki & (vals[c][:, i] > best_score[c] + TOL[c])
+            if upd.any():
+                best_score[c] = np.where(upd, vals[c][:, i], best_score[c])
+                best_index[c][upd] = i
+    out = []
+    for u in range(U):
+        best = {}
+        for c in TOL:
+            i = int(best_index[c][u])
+            if i < 0:
+                best[c] = {"index": None, "score": -1, "params": {}}
+            else:
+                best[c] = {"index": i, "score": float(vals[c][u, i]), "params": dict(points[i]),
+                           "stoi": float(stoi[u, i]), "pesq": float(pq[u, i]), "snr": float(snr[u, i])}
+        out.append(best)
+    return out

@@ -8,7 +8,7 @@ score tables (and, optionally, the reference's three winners per (utterance, alg
 import numpy as np
 
 from .engine import DEFAULT_CHUNK_ITEMS, SweepEngine
-from .grid import grid_points, select_best
+from .grid import grid_points, select_best, select_best_batch
 from .parameter_ranges import (param_ranges_mmse, param_ranges_omlsa, param_ranges_ss,
                                param_ranges_wiener)
 
@@ -61,17 +61,17 @@ def run_engine(engine, grids=DEFAULT_GRIDS):
 
 
 def select_all(scores, points, pesq=None):
-    """The reference's three winners per (utterance, algorithm), by its sequential scan.
-    ``pesq[alg][u][i]`` may be injected; otherwise PESQ is 0.0 (see speech_enhancement_comparison)."""
+    """The reference's three winners per (utterance, algorithm), by its sequential scan (vectorised over
+    utterances).  ``pesq[alg][u][i]`` may be injected (None entries = candidate skipped); otherwise PESQ is
+    0.0 (see speech_enhancement_comparison)."""
     out = {}
     for name, sc in scores.items():
-        rows = []
-        for u in range(sc.shape[0]):
-            valid = (sc[u]["flags"] & 1) != 0
-            snr = [float("inf") if f & 4 else float(v) for v, f in zip(sc[u]["snr"], sc[u]["flags"])]
-            pq = pesq[name][u] if pesq is not None else [0.0] * sc.shape[1]
-            rows.append(select_best(points[name], [float(v) for v in sc[u]["stoi"]], pq, snr, valid))
-        out[name] = rows
+        valid = (sc["flags"] & 1) != 0
+        snr = np.where((sc["flags"] & 4) != 0, np.inf, sc["snr"].astype(np.float64))
+        pq = None
+        if pesq is not None:
+            pq = np.array([[np.nan if v is None else float(v) for v in row] for row in pesq[name]], dtype=np.float64)
+        out[name] = select_best_batch(points[name], sc["stoi"].astype(np.float64), pq, snr, valid)
     return out
 
 

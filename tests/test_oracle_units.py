@@ -105,3 +105,29 @@ def test_alignment_lag_detects_shift():
     shifted = np.concatenate([np.zeros(37), n])[:len(n)]       # delayed by 37 -> lag -37
     assert oracle.alignment_lag(c, shifted, 16000) == -37
     assert oracle.alignment_lag(c[:200], n[:200], 16000) is None
+
+
+def test_vectorised_selection_equals_the_sequential_scan():
+    """sweep.select_all scans all utterances at once; it must reproduce grid.select_best (the reference's
+    hysteresis scan, speech_enhancement_comparison.py:186-216) exactly, including ties, near-ties below the
+    tolerances, invalid candidates and skipped (PESQ None) candidates."""
+    import numpy as np
+    from classical_speech_enhancement_b200 import parameter_ranges as pr
+    from classical_speech_enhancement_b200.grid import grid_points as gp, select_best as sb, select_best_batch
+    pts = gp(pr.param_ranges_wiener)
+    rng = np.random.default_rng(7)
+    U, P = 12, len(pts)
+    stoi = np.round(rng.uniform(0.5, 0.9, (U, P)), 2).astype(np.float32) + (rng.integers(0, 3, (U, P)) * 5e-7).astype(np.float32)
+    snr = rng.normal(5, 3, (U, P)).astype(np.float32)
+    snr[0, 3] = np.inf
+    valid = rng.random((U, P)) > 0.1
+    valid[1] = False                                                     # an utterance without any valid candidate
+    pesq = [[None if rng.random() < 0.05 else float(np.round(rng.uniform(1, 3), 2)) for _ in range(P)] for _ in range(U)]
+    pq = np.array([[np.nan if v is None else v for v in row] for row in pesq])
+    batch = select_best_batch(pts, stoi.astype(np.float64), pq, snr.astype(np.float64), valid)
+    for u in range(U):
+        assert batch[u] == sb(pts, [float(v) for v in stoi[u]], pesq[u], [float(v) for v in snr[u]], valid[u])
+    assert batch[1]["stoi"]["index"] is None
+    nop = select_best_batch(pts, stoi.astype(np.float64), None, snr.astype(np.float64), valid)
+    for u in range(U):
+        assert nop[u] == sb(pts, [float(v) for v in stoi[u]], [0.0] * P, [float(v) for v in snr[u]], valid[u])
