@@ -237,6 +237,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    args.warmup = max(args.warmup, 3)          # timing rule: at least three untimed steps (the JSON reports the value used)
+    args.steps = max(args.steps, 1)
 
     import torch
     import torch.distributed as dist
