@@ -45,9 +45,15 @@ SIGNATURES = {
     "cse_align_items": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "cse_stoi_items": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "cse_expand_scores": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "cse_select_best": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "cse_debug_special": (_i, [_i, _vp, _vp, _i]),
     "cse_sweep": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _sz, _vp]),
 }
+
+
+#: cse_winner_t (include/cse.h)
+WINNER_DTYPE = np.dtype([("index", np.int32), ("lag", np.int32), ("flags", np.int32), ("reserved", np.int32),
+                         ("score", np.float64), ("stoi", np.float64), ("pesq", np.float64), ("snr", np.float64)])
 
 
 class CseLibraryError(RuntimeError):
@@ -85,6 +91,7 @@ class CseLibrary:
         self.real_bits = self._dll.cse_dtype()
         self.real = np.float64 if self.real_bits == 64 else np.float32
         self.score_dtype = np.dtype([("stoi", self.real), ("snr", self.real), ("lag", np.int32), ("flags", np.int32)])
+        self.winner_dtype = WINNER_DTYPE
 
     def last_error(self):
         return self._dll.cse_last_error().decode("utf-8", "replace")

@@ -9,6 +9,7 @@
 #include "k_noise.cuh"
 #include "k_score.cuh"
 #include "k_stoi_stream.cuh"
+#include "k_select.cuh"
 
 #include <mutex>
 #include <cstdarg>

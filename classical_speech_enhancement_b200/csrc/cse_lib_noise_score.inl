@@ -257,6 +257,15 @@ extern "C" int cse_expand_scores(const cse_score_t* unique_scores, const int* ba
     return check_launch("expand_scores");
 }
 
+// ------------------------------------------------------------------ K6 selection
+extern "C" int cse_select_best(const cse_score_t* table, const double* pesq, int n_utts, int n_points,
+                               cse_winner_t* winners, void* stream) {
+    CSE_REQUIRE(table && winners, "NULL argument");
+    CSE_REQUIRE(n_utts > 0 && n_points > 0, "bad sizes");
+    CSE_LAUNCH(select_best_kernel, n_utts, 32 * CSE_SEL_CRITERIA, 0, stream, table, pesq, n_points, winners);
+    return check_launch("select_best");
+}
+
 // ------------------------------------------------------------------ host-side probes for tests
 // Evaluates the gain rules' special-function fits on the host (same code the kernels inline).
 extern "C" int cse_debug_special(int which, const double* x, double* y, int n) {

@@ -68,7 +68,7 @@ def gather_device_scores(engine, items, n_utts, device=None):
     scores = {}
     for name, pts, buf, pl in items:
         if world == 1:
-            scores[name] = engine.table_to_host(engine.be.view_bytes_as(buf, np.uint8), pl, engine.U)
+            scores[name] = engine.table_to_host(engine.be.view_bytes_as(buf, np.uint8, tag=(name, "table")), pl, engine.U)
             continue
         send = buf if isinstance(buf, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(buf))
         recv = torch.empty((world,) + tuple(send.shape), dtype=torch.uint8, device=send.device)
@@ -76,7 +76,7 @@ def gather_device_scores(engine, items, n_utts, device=None):
             dist.all_gather_into_tensor(recv, send)
         else:
             dist.all_gather(list(recv.unbind(0)), send)
-        host = (engine.be.staged_to_host(recv) if recv.is_cuda and hasattr(engine.be, "staged_to_host") else recv.cpu().numpy().reshape(-1)).reshape(world, -1)
+        host = (engine.be.staged_to_host(recv, tag=(name, "gathered")) if recv.is_cuda and hasattr(engine.be, "staged_to_host") else recv.cpu().numpy().reshape(-1)).reshape(world, -1)
         if all(b[r + 1] - b[r] == b[1] - b[0] for r in range(world)):
             scores[name] = host.reshape(-1).view(engine.lib.score_dtype).reshape(n_utts, pl["n_points"])   # zero copy
         else:
@@ -84,12 +84,54 @@ def gather_device_scores(engine, items, n_utts, device=None):
     return scores
 
 
-def sweep_sharded(clean, noisy, grids=None, select=True, chunk_items=DEFAULT_CHUNK_ITEMS, device=None, engine_kwargs=None):
-    """Each rank sweeps its block of utterances; every rank returns the full gathered tables.
-    ``clean`` / ``noisy`` are the full host arrays [U, L] (each rank slices its block)."""
+def gather_winners(engine, winners_dev, n_utts, u_pad):
+    """all_gather of every algorithm's per-rank winners ({alg: device ``cse_winner_t`` [U_local][3]}) in ONE
+    collective: 48-byte records, ~0.6 KB per utterance for four algorithms - instead of the per-point
+    score tables (156 KB per utterance).  Returns {alg: host array [n_utts, 3]} on every rank."""
+    import torch
+    import torch.distributed as dist
+    names = list(winners_dev)
+    wdt = engine.lib.winner_dtype
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return {name: engine.winners_to_host(winners_dev[name], tag=(name, "winners")).copy() for name in names}
+    b = shard_bounds(n_utts, world)
+    rec = 3 * wdt.itemsize
+    is_torch = isinstance(winners_dev[names[0]], torch.Tensor)
+    if is_torch:
+        send = torch.zeros((len(names), u_pad * rec), dtype=torch.uint8, device=winners_dev[names[0]].device)
+        for k, name in enumerate(names):
+            send[k, :engine.U * rec] = winners_dev[name].reshape(-1).view(torch.uint8)[:engine.U * rec]
+    else:
+        host = np.zeros((len(names), u_pad * rec), dtype=np.uint8)
+        for k, name in enumerate(names):
+            host[k, :engine.U * rec] = np.asarray(winners_dev[name]).reshape(-1).view(np.uint8)[:engine.U * rec]
+        send = torch.from_numpy(host)
+    recv = torch.empty((world,) + tuple(send.shape), dtype=torch.uint8, device=send.device)
+    if send.is_cuda:
+        dist.all_gather_into_tensor(recv, send)
+    else:
+        dist.all_gather(list(recv.unbind(0)), send)
+    host = recv.cpu().numpy()
+    out = {}
+    for k, name in enumerate(names):
+        out[name] = np.concatenate([host[r, k, :(b[r + 1] - b[r]) * rec].view(wdt).reshape(-1, 3) for r in range(world)])
+    return out
+
+
+def sweep_sharded(clean, noisy, grids=None, select=True, chunk_items=DEFAULT_CHUNK_ITEMS, device=None, engine_kwargs=None,
+                  tables=False, pesq=None, pesq_scorer=None, pesq_workers=None):
+    """Each rank sweeps its block of utterances AND runs the selection scan for them on its own device; the
+    only exchange is one all_gather of the winners' records (every rank returns the winners of all
+    utterances).  ``tables=True`` additionally all-gathers the per-point score tables (128 MB for the
+    824-utterance job) - for callers that want every candidate's score on every rank.
+    ``clean`` / ``noisy`` are the full host arrays [U, L] (each rank slices its block); ``pesq`` =
+    {alg: [U][P]} for the full dataset (each rank slices its rows), or ``pesq_scorer`` to have each rank's
+    candidates scored by its own host process pool while its sweep runs (:mod:`.pesq_pool`)."""
+    import warnings
     import torch.distributed as dist
     from . import sweep as sw
-    from .engine import DEFAULT_CHUNK_ITEMS, SweepEngine
+    from .engine import SweepEngine
     grids = grids or sw.DEFAULT_GRIDS
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
@@ -99,10 +141,20 @@ def sweep_sharded(clean, noisy, grids=None, select=True, chunk_items=DEFAULT_CHU
     b = shard_bounds(n_utts, world)
     u_pad = max(b[r + 1] - b[r] for r in range(world))
     sl = slice(b[rank], b[rank + 1])
-    eng = SweepEngine(clean[sl], noisy[sl], chunk_items=chunk_items, **(engine_kwargs or {}))
-    items = sw.run_engine_device(eng, grids, u_pad=u_pad)
-    scores = gather_device_scores(eng, items, n_utts, device=device)
+    local_pesq = None if pesq is None else {name: sw._pesq_array(pesq[name])[sl] for name in pesq}
+    if pesq_scorer is not None:
+        eng = SweepEngine(clean[sl], noisy[sl], chunk_items=min(chunk_items, sw.PESQ_CHUNK_ITEMS), **(engine_kwargs or {}))
+        items, local_pesq = sw.run_engine_device_with_pesq(eng, pesq_scorer, grids, u_pad=u_pad, pesq_workers=pesq_workers)
+        pesq = local_pesq
+    else:
+        eng = SweepEngine(clean[sl], noisy[sl], chunk_items=chunk_items, **(engine_kwargs or {}))
+        items = sw.run_engine_device(eng, grids, u_pad=u_pad)
     points = {name: pts for name, pts, _, _ in items}
-    return {"scores": scores, "points": points,
-            "selection": sw.select_all(scores, points) if select else None,
-            "local_engine": eng}
+    winners = selection = None
+    if select:
+        winners = gather_winners(eng, sw.select_winners_device(eng, items, local_pesq), n_utts, u_pad)
+        if pesq is None:
+            warnings.warn("selection without PESQ: only the 'stoi' winner is available", stacklevel=2)
+        selection = sw.selection_from_winners(points, winners, pesq is not None)
+    scores = gather_device_scores(eng, items, n_utts, device=device) if tables else None
+    return {"scores": scores, "points": points, "winners": winners, "selection": selection, "local_engine": eng}

@@ -90,17 +90,19 @@ class TorchCudaBackend:
         e.record(self.torch.cuda.current_stream(self.device))
         return e
 
-    def view_bytes_as(self, buf, dtype):
-        return self.staged_to_host(buf).view(dtype)
+    def view_bytes_as(self, buf, dtype, tag=None):
+        return self.staged_to_host(buf, tag=tag).view(dtype)
 
-    def staged_to_host(self, buf):
+    def staged_to_host(self, buf, tag=None):
         """Device tensor -> numpy bytes.  With ``reuse_result_buffers`` (set by throughput drivers that consume
-        a step's tables before the next step) the copy lands in a process-wide pinned staging buffer of that
-        size, which the next copy of the same size overwrites; otherwise in a fresh pageable array."""
+        a step's tables before the next step) the copy lands in a process-wide pinned staging buffer keyed by
+        (device, size, tag), which the next copy with the same key overwrites; otherwise in a fresh pageable
+        array.  ``tag`` names the result (algorithm, kind) so that two equally sized results of ONE step never
+        share a buffer."""
         flat = buf.reshape(-1).view(self.torch.uint8)
         if not _runtime.get("reuse_result_buffers"):
             return flat.cpu().numpy()
-        key = (self.device.index, flat.numel())
+        key = (self.device.index, flat.numel(), tag)
         host = _PINNED_POOL.get(key)
         if host is None:
             host = self.torch.empty((flat.numel(),), dtype=self.torch.uint8, pin_memory=True)
@@ -111,6 +113,42 @@ class TorchCudaBackend:
 
     def slice_rows(self, buf, start, stop):
         return buf[start:stop]
+
+    # --- chunk export on a side stream (PESQ path: candidate waveforms leave the device while the next chunk runs)
+    def export_begin(self, parts, slot):
+        """Enqueue device->host copies of ``parts`` = [(tensor, byte offset, nbytes)] on the copy stream, ordered
+        after the work already enqueued on the current stream; pinned staging buffers are recycled per ``slot``."""
+        t = self.torch
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = t.cuda.Stream(device=self.device)
+            self._export_pinned = {}
+        main = t.cuda.current_stream(self.device)
+        ready = t.cuda.Event()
+        ready.record(main)
+        self._copy_stream.wait_event(ready)
+        hosts = []
+        with t.cuda.stream(self._copy_stream):
+            for k, (buf, off, nbytes) in enumerate(parts):
+                key = (slot, k)
+                host = self._export_pinned.get(key)
+                if host is None or host.numel() < nbytes:
+                    host = self._export_pinned[key] = t.empty((nbytes,), dtype=t.uint8, pin_memory=True)
+                src = buf.reshape(-1).view(t.uint8)[off:off + nbytes]
+                host[:nbytes].copy_(src, non_blocking=True)
+                hosts.append((host, nbytes))
+            done = t.cuda.Event()
+            done.record(self._copy_stream)
+        return (hosts, done)
+
+    def export_wait(self, handle):
+        """Host arrays (fresh copies, the pinned buffers are reused) of a finished export."""
+        hosts, done = handle
+        done.synchronize()
+        return [host[:n].numpy().copy() for host, n in hosts]
+
+    def export_fence(self, handle):
+        """The current stream may not overwrite the exported buffers before the copy has finished."""
+        self.torch.cuda.current_stream(self.device).wait_event(handle[1])
 
 
 class SweepEngine:
@@ -133,7 +171,8 @@ class SweepEngine:
         be, lib_ = self.be, self.lib
         self.tables = be.empty((lib_.tables_bytes(),), np.uint8)
         lib_.tables_init(be.ptr(self.tables), be.stream())
-        self.clean = be.from_host(np.ascontiguousarray(clean, dtype=self.real))
+        self.clean_host = np.ascontiguousarray(clean, dtype=self.real)      # kept for the host-side PESQ pool
+        self.clean = be.from_host(self.clean_host)
         self.noisy = be.from_host(np.ascontiguousarray(noisy, dtype=self.real))
         self.h2d_bytes = 2 * clean.size * np.dtype(self.real).itemsize
         self._stft = {}
@@ -141,6 +180,7 @@ class SweepEngine:
         self._noise = {}
         self._ws = {}
         self._plans = {}
+        self._exports = []
         self.launches = 0
         self.cache = None
         self.sr = sr
@@ -283,7 +323,7 @@ class SweepEngine:
             member_idx = np.concatenate([np.asarray(m, dtype=np.int64) for m in g["members"]])
             row_idx = np.concatenate([np.full(len(m), r, dtype=np.int64) for r, m in enumerate(g["members"])])
             info.append({"key": gkey, "rows": g["rows"], "params_host": _lib.pack_params(g["rows"]), "n_rows": n_rows,
-                         "col0": col, "member_idx": member_idx, "row_idx": row_idx})
+                         "col0": col, "member_idx": member_idx, "row_idx": row_idx, "members": g["members"]})
             col += n_rows
         out = {"groups": info, "unique": col, "n_points": len(points)}
         _PLAN_CACHE[key] = (points, out)
@@ -291,8 +331,12 @@ class SweepEngine:
         self._plans[key] = pl
         return pl
 
-    def sweep_device(self, alg_name, points, u_pad=None):
+    def sweep_device(self, alg_name, points, u_pad=None, chunk_sink=None):
         """Enqueue the whole sweep of one algorithm; returns (device table, plan).
+
+        ``chunk_sink(group, item0, wav, records)``, if given, receives every chunk's raw candidate waveforms
+        ([n][L], host) and score records (lag, flags, ...) - the feed of the host-side PESQ pool.  The copies run on
+        a side stream from one of two alternating waveform buffers while the next chunk is computed.
 
         The device table is the NOMINAL score table [u_pad][n_points] of 16-byte records (u_pad >= U
         rows so that equally sized tables can be all-gathered across ranks; rows >= U are zero).
@@ -319,11 +363,17 @@ class SweepEngine:
             sc_ptr = be.ptr_at(uniq, self.U * g["col0"] * rec)          # group block [U][n_rows]
             total = self.U * n_rows
             chunk = min(self.chunk_items, total)
-            wav = self._workspace("wav", chunk * self.L * np.dtype(self.real).itemsize)
+            rb = np.dtype(self.real).itemsize
+            wavs = [self._workspace("wav", chunk * self.L * rb)]
+            if chunk_sink is not None:
+                wavs.append(self._workspace("wav1", chunk * self.L * rb))
             nbytes = lib_.score_workspace_bytes(chunk, self.L, SR)
             ws = self._workspace("score", nbytes)
-            for i0 in range(0, total, chunk):
+            for k, i0 in enumerate(range(0, total, chunk)):
                 n = min(chunk, total - i0)
+                wav = wavs[k % len(wavs)]
+                if chunk_sink is not None:
+                    self._export_retire(chunk_sink, keep=1)     # chunk k-2 used this buffer: its copy must be over
                 t0 = self._tick()
                 lib_.enhance_items(be.ptr(self.tables), alg, be.ptr(Y), be.ptr(N), int(tv), self.L, n_fft, hop,
                                    be.ptr(params), n_rows, i0, n, be.ptr(wav), be.stream())
@@ -338,6 +388,14 @@ class SweepEngine:
                 self._record(("align", alg, n_fft, hop, key[2]), n, t1, t2)
                 self._record(("stoi", alg, n_fft, hop, key[2]), n, t2, t3)
                 self.launches += 3
+                if chunk_sink is not None:
+                    parts = [(wav, 0, n * self.L * rb), (uniq, (self.U * g["col0"] + i0) * rec, n * rec)]
+                    handle = be.export_begin(parts, slot=k % 2) if hasattr(be, "export_begin") else [
+                        np.array(be.to_host(wav).reshape(-1).view(np.uint8)[:parts[0][2]]),
+                        np.array(be.to_host(uniq).reshape(-1).view(np.uint8)[parts[1][1]:parts[1][1] + parts[1][2]])]
+                    self._exports.append((handle, g, i0, n))
+            if chunk_sink is not None:
+                self._export_retire(chunk_sink, keep=0)
         table = (be.zeros if u_pad > self.U else be.empty)((u_pad * pl["n_points"] * rec,), np.uint8)
         if "dev_maps" not in pl or pl["dev_maps"][0] != self.U:
             base = np.zeros(pl["n_points"], dtype=np.int32)
@@ -353,10 +411,45 @@ class SweepEngine:
         self.last_unique = pl["unique"]
         return table, pl
 
+    def _export_retire(self, sink, keep):
+        """Hand finished chunk exports to the sink until at most ``keep`` are in flight."""
+        be = self.be
+        while len(self._exports) > keep:
+            handle, g, i0, n = self._exports.pop(0)
+            if hasattr(be, "export_wait"):
+                be.export_fence(handle)
+                wav_b, rec_b = be.export_wait(handle)
+            else:
+                wav_b, rec_b = handle
+            sink(g, i0, wav_b.view(self.real).reshape(n, self.L), rec_b.view(self.lib.score_dtype))
+
     def table_to_host(self, raw_bytes, pl, u_rows):
         """[u_pad][n_points] record bytes -> structured array [u_rows, n_points]."""
         dt = self.lib.score_dtype
         return np.asarray(raw_bytes).reshape(-1).view(dt).reshape(-1, pl["n_points"])[:u_rows]
+
+    def select_device(self, table, n_points, pesq=None):
+        """Enqueue the reference's three-way sequential selection (``speech_enhancement_comparison.py:186-216``)
+        over a nominal device table [>= U][n_points]; returns the device buffer of ``cse_winner_t`` [U][3]
+        (stoi, pesq, balance).  ``pesq``: host array [U, n_points] of float64 (NaN = candidate skipped) or None
+        (PESQ = 0.0 everywhere: only the ``stoi`` winner is meaningful)."""
+        be, lib_ = self.be, self.lib
+        win = be.empty((self.U * 3 * lib_.winner_dtype.itemsize,), np.uint8)
+        pq = None
+        if pesq is not None:
+            pesq = np.ascontiguousarray(pesq, dtype=np.float64)
+            if pesq.shape != (self.U, n_points):
+                raise ValueError(f"pesq must be [U, n_points] = {(self.U, n_points)}, got {pesq.shape}")
+            pq = be.from_host(pesq)
+        lib_.select_best(be.ptr(table), be.ptr(pq), self.U, int(n_points), be.ptr(win), be.stream())
+        self.launches += 1
+        self._keepalive_sel = pq
+        return win
+
+    def winners_to_host(self, win, tag=None):
+        """Device winners buffer -> structured array [U, 3] of ``_lib.WINNER_DTYPE``."""
+        return np.asarray(self.be.view_bytes_as(win, np.uint8, **({"tag": tag} if tag is not None else {}))).view(
+            self.lib.winner_dtype).reshape(-1, 3)[:self.U]
 
     def sweep(self, alg_name, points):
         """Scores of every grid point for every utterance.

@@ -110,6 +110,27 @@ def select_best(points, stoi, pesq, snr, valid):
     return best
 
 
+CRITERIA = tuple(TOL)      # record order of cse_winner_t rows: stoi, pesq, balance
+
+
+def best_from_winners(points, wrow, pesq_available=True):
+    """One utterance's ``cse_winner_t[3]`` (device selection, ``cse_select_best``) -> the dict ``select_best``
+    returns.  Without PESQ the ``pesq`` / ``balance`` entries are marked unavailable instead of carrying the
+    meaningless "first valid point" a constant PESQ of 0.0 would select."""
+    best = {}
+    for k, c in enumerate(CRITERIA):
+        w = wrow[k]
+        i = int(w["index"])
+        if c != "stoi" and not pesq_available:
+            best[c] = {"index": None, "score": None, "params": {}, "unavailable": "PESQ was not computed"}
+        elif i < 0:
+            best[c] = {"index": None, "score": -1, "params": {}}
+        else:
+            best[c] = {"index": i, "score": float(w["score"]), "params": dict(points[i]), "stoi": float(w["stoi"]),
+                       "pesq": float(w["pesq"]), "snr": float(w["snr"]), "lag": int(w["lag"])}
+    return best
+
+
 def select_best_batch(points, stoi, pesq, snr, valid):
     """``select_best`` for U utterances at once: the scan is sequential over the grid (hysteresis makes
     it order-dependent) but independent per utterance, so every step is one vector operation over the

@@ -6,8 +6,9 @@ Python loop; the three winners are then chosen on the host by the reference's se
 hysteresis scan, in grid order, and only the winners' waveforms are re-materialised.
 
 PESQ: the reference scores every candidate with the ``pesq`` C extension (``:178``).  When that
-package is importable this module does the same (host, process pool) for exact parity of all three
-selections.  When it is not (this image), ``pesq_scorer`` must be injected, or PESQ is taken as 0.0
+package is importable this module does the same - the candidates' finalized waveforms are handed slab-wise
+to a host process pool (:mod:`.pesq_pool`) while the device computes the next slab - for exact parity of
+all three selections; any ``scorer(clean, wav, sr)`` can be injected in its place.  When it is not (this image), ``pesq_scorer`` must be injected, or PESQ is taken as 0.0
 for every candidate with a warning: the ``stoi`` winner is then exact, the ``pesq``/``balance``
 winners are not comparable with the reference.
 """
@@ -21,7 +22,7 @@ from scipy.signal import correlate
 
 from .engine import SweepEngine, finalize_host
 from .evaluation_metrics import calculate_combined_speech_score, calculate_pesq
-from .grid import ALGORITHM_IDS, grid_points, select_best
+from .grid import ALGORITHM_IDS, best_from_winners, grid_points  # noqa: F401
 from .parameter_ranges import (param_ranges_mmse, param_ranges_omlsa, param_ranges_ss,  # noqa: F401
                                param_ranges_wiener)
 
@@ -101,22 +102,87 @@ def finalize_enhanced(enhanced, clean_ref, sr, do_align=True):
     return finalize_host(enhanced, int(sc["lag"]), len(clean_ref))
 
 
-def _resolve_algorithm(algorithm_function):
+def _resolve_algorithm(algorithm_function, _depth=0):
+    """Which of the four device algorithms a callable stands for, or None.
+
+    The reference hands ``optimize_parameters`` a closure (``algorithm_wrapper``, ``:282-294``) around the real
+    entry point, so the callable is unwrapped the ways Python offers: the ``__cse_algorithm__`` tag this
+    package's entry points carry, ``functools.wraps`` / ``partial`` chains, and the free variables of a closure."""
+    if algorithm_function is None or _depth > 4:
+        return None
     name = getattr(algorithm_function, "__cse_algorithm__", None)
-    if name is None:
-        raise TypeError("optimize_parameters needs one of this package's four algorithm functions "
-                        "(spectral_subtraction, wiener_filter, mmse, advanced_mmse) or a wrapper "
-                        "carrying their __cse_algorithm__ attribute")
-    return name
+    if name is not None:
+        return name
+    for attr in ("__wrapped__", "func"):
+        inner = getattr(algorithm_function, attr, None)
+        if callable(inner):
+            name = _resolve_algorithm(inner, _depth + 1)
+            if name is not None:
+                return name
+    found = {_resolve_algorithm(c.cell_contents, _depth + 1) for c in (getattr(algorithm_function, "__closure__", None) or ())
+             if _cell_is_callable(c)}
+    found.discard(None)
+    return found.pop() if len(found) == 1 else None
 
 
-def _pesq_scores(clean, waveforms, sr, pesq_scorer):
-    return [pesq_scorer(clean, w, sr) for w in waveforms]
+def _cell_is_callable(cell):
+    try:
+        return callable(cell.cell_contents)
+    except ValueError:          # empty cell
+        return False
+
+
+def _sweep_foreign_callable(eng, algorithm_function, clean, noisy, sr, points):
+    """``optimize_parameters`` for a callable that is none of the device algorithms: the reference's own loop -
+    one call per grid point (``:165``) - with finalize / STOI / SNR of the returned waveforms batched on the
+    device.  Returns (score records [P], {index: finalized waveform})."""
+    sc = np.zeros(len(points), dtype=eng.lib.score_dtype)
+    finalized = {}
+    slab_idx, slab = [], []
+
+    def flush():
+        if slab:
+            out = eng.score_waveforms(np.stack(slab)[None], finalize=True)[0]
+            for j, i in enumerate(slab_idx):
+                sc[i] = out[j]
+                if out[j]["flags"] & 1:
+                    finalized[i] = finalize_host(slab[j], int(out[j]["lag"]), len(clean))
+            slab_idx.clear()
+            slab.clear()
+
+    for i, p in enumerate(points):
+        try:
+            enhanced = algorithm_function(noisy, sr, **p)
+            if enhanced is None or len(enhanced) == 0:
+                continue
+            enhanced = to_mono(np.asarray(enhanced, dtype=np.float64))
+        except Exception as e:                                    # the reference prints and skips (:226-228)
+            print(f" Warning with params {p}: {e}")
+            continue
+        if len(enhanced) == len(clean):
+            slab_idx.append(i)
+            slab.append(enhanced)
+            if len(slab) == 64:
+                flush()
+        else:                                                     # other lengths: host finalize (:92-106), device scoring
+            fin = finalize_enhanced(enhanced, clean, sr, do_align=True)
+            if fin is not None:
+                one = eng.score_waveforms(fin[None, None, :], finalize=False)[0, 0]
+                sc[i] = one
+                sc[i]["flags"] |= 1
+                finalized[i] = fin
+    flush()
+    return sc, finalized
 
 
 def optimize_parameters(clean_reference, noisy_audio, sr, algorithm_function, param_ranges, *,
-                        pesq_scorer="auto", engine=None, verbose=True) -> Dict[str, Any]:
+                        pesq_scorer="auto", pesq_workers=None, engine=None, verbose=True) -> Dict[str, Any]:
     """Brute-force grid search for STOI, PESQ and balance winners (reference ``:109-252``).
+
+    ``algorithm_function`` may be one of this package's four entry points, the reference's
+    ``algorithm_wrapper`` closure around one (or any ``functools.wraps`` / ``partial`` wrapper): the whole grid
+    then runs as one batched device sweep.  Any other callable is executed one grid point at a time, as the
+    reference does, with a warning; finalize and scoring still run on the device.
 
     Returns the reference's dict: ``stoi`` / ``pesq`` / ``balance`` (score, params, enhanced, the
     other metrics, snr), ``baseline`` and ``improvements``."""
@@ -144,31 +210,46 @@ def optimize_parameters(clean_reference, noisy_audio, sr, algorithm_function, pa
     baseline_snr = (float("inf") if base["flags"] & 4 else float(base["snr"])) or 0
     baseline_comp = calculate_combined_speech_score(baseline_stoi, baseline_pesq)
 
-    sc = eng.sweep(alg_name, points)[0]
-    valid = (sc["flags"] & 1) != 0
-    stoi = [float(v) for v in sc["stoi"]]
-    snr = [float("inf") if f & 4 else float(v) for v, f in zip(sc["snr"], sc["flags"])]
-    if scorer is None:
-        pesq_vals = [0.0] * len(points)
+    foreign = None
+    if alg_name is None:
+        warnings.warn("optimize_parameters: the callable is not one of the device algorithms (or a wrapper around "
+                      "one); running it one grid point at a time as the reference does")
+        sc, foreign = _sweep_foreign_callable(eng, algorithm_function, clean, noisy, sr, points)
+        table_dev = eng.be.from_host(sc.view(np.uint8).reshape(-1))
     else:
-        # the reference scores every candidate with PESQ; waveforms are re-materialised in slabs
-        pesq_vals = [None] * len(points)
-        slab = 64
-        for s0 in range(0, len(points), slab):
-            idx = [i for i in range(s0, min(s0 + slab, len(points))) if valid[i]]
-            if not idx:
-                continue
-            wav = eng.enhance(alg_name, [points[i] for i in idx])[0]
-            for j, i in enumerate(idx):
-                pesq_vals[i] = scorer(clean, finalize_host(wav[j], int(sc["lag"][i]), len(clean)), sr)
-    best = select_best(points, stoi, pesq_vals, snr, valid)
+        table_dev, _ = eng.sweep_device(alg_name, points)
+        sc = eng.table_to_host(eng.be.view_bytes_as(table_dev, np.uint8), {"n_points": len(points)}, 1)[0]
+    valid = (sc["flags"] & 1) != 0
+    pesq_tab = None
+    if scorer is not None:
+        # the reference scores every candidate with PESQ (:178): waveforms are re-materialised in slabs on
+        # the device and scored by a host process pool while the next slab is computed
+        from .pesq_pool import PesqPool
+        with PesqPool(scorer, sr, workers=pesq_workers) as pool:
+            slab = 64
+            for s0 in range(0, len(points), slab):
+                idx = [i for i in range(s0, min(s0 + slab, len(points))) if valid[i]]
+                if not idx:
+                    continue
+                if foreign is not None:
+                    wavs = [foreign[i] for i in idx]
+                else:
+                    raw = eng.enhance(alg_name, [points[i] for i in idx])[0]
+                    wavs = [finalize_host(raw[j], int(sc["lag"][i]), len(clean)) for j, i in enumerate(idx)]
+                pool.submit(0, idx, clean, wavs)
+            pesq_tab = pool.table(1, len(points))
+    win = eng.winners_to_host(eng.select_device(table_dev, len(points), pesq_tab))[0]
+    best = best_from_winners(points, win)
 
     for key in ("stoi", "pesq", "balance"):
         if best[key]["index"] is None:
             raise ValueError(f"Optimization failed for {key} - no valid parameters found!")
     winners = sorted({best[k]["index"] for k in best})
-    wav = eng.enhance(alg_name, [points[i] for i in winners])[0]
-    final = {i: finalize_host(wav[j], int(sc["lag"][i]), len(clean)) for j, i in enumerate(winners)}
+    if foreign is not None:
+        final = {i: foreign[i] for i in winners}
+    else:
+        wav = eng.enhance(alg_name, [points[i] for i in winners])[0]
+        final = {i: finalize_host(wav[j], int(sc["lag"][i]), len(clean)) for j, i in enumerate(winners)}
 
     def pack(key, others):
         b = best[key]

@@ -5,10 +5,12 @@
 it takes HOST arrays, moves them to the device once, runs the device sweep and returns the
 score tables (and, optionally, the reference's three winners per (utterance, algorithm)).
 """
+import warnings
+
 import numpy as np
 
 from .engine import DEFAULT_CHUNK_ITEMS, SweepEngine
-from .grid import grid_points, select_best, select_best_batch
+from .grid import best_from_winners, grid_points, select_best_batch
 from .parameter_ranges import (param_ranges_mmse, param_ranges_omlsa, param_ranges_ss,
                                param_ranges_wiener)
 
@@ -50,43 +52,129 @@ def run_engine_device(engine, grids=DEFAULT_GRIDS, u_pad=None):
     return out
 
 
+def run_engine_device_with_pesq(engine, pesq_scorer, grids=DEFAULT_GRIDS, u_pad=None, pesq_workers=None):
+    """:func:`run_engine_device` + host PESQ of EVERY candidate (``speech_enhancement_comparison.py:178``): each
+    chunk's waveforms are copied out on a side stream while the next chunk runs and scored by a process pool.
+    Returns (items, {alg: float64 [U, P] PESQ table, NaN = skipped})."""
+    from .pesq_pool import PesqPool
+    out, tables = [], {}
+    for name, ranges in grids:
+        pts = cached_points(name, ranges)
+        with PesqPool(pesq_scorer, engine.sr, workers=pesq_workers) as pool:
+            def sink(g, i0, wav, recs, pool=pool):
+                n_rows, members = g["n_rows"], g["members"]
+                j = 0
+                while j < len(recs):                                   # runs of items of one utterance
+                    u = (i0 + j) // n_rows
+                    j1 = min(len(recs), (u + 1) * n_rows - i0)
+                    rows = [(i0 + k) % n_rows for k in range(j, j1)]
+                    pool.submit(u, [members[r] for r in rows], engine.clean_host[u], wav[j:j1], recs["lag"][j:j1],
+                                recs["flags"][j:j1])
+                    j = j1
+            buf, pl = engine.sweep_device(name, pts, u_pad=u_pad, chunk_sink=sink)
+            tables[name] = pool.table(engine.U, len(pts))
+        out.append((name, pts, buf, pl))
+    return out, tables
+
+
 def run_engine(engine, grids=DEFAULT_GRIDS):
     """Device part + one device->host copy per algorithm: {alg: structured scores [U, n_points]} (+ points)."""
     scores, points, unique = {}, {}, 0
     for name, pts, buf, pl in run_engine_device(engine, grids):
-        scores[name] = engine.table_to_host(engine.be.view_bytes_as(buf, np.uint8), pl, engine.U)
+        scores[name] = engine.table_to_host(engine.be.view_bytes_as(buf, np.uint8, tag=(name, "table")), pl, engine.U)
         points[name] = pts
         unique += pl["unique"]
     return scores, points, unique
 
 
+def _pesq_array(pesq_rows):
+    """[[float | None]] -> float64 [U, P] with NaN where ``calculate_pesq`` returned None (candidate skipped)."""
+    if isinstance(pesq_rows, np.ndarray) and pesq_rows.dtype == np.float64:
+        return pesq_rows
+    return np.array([[np.nan if v is None else float(v) for v in row] for row in pesq_rows], dtype=np.float64)
+
+
+def _mark_pesq_unavailable(best):
+    for c in ("pesq", "balance"):
+        best[c] = {"index": None, "score": None, "params": {}, "unavailable": "PESQ was not computed"}
+    return best
+
+
 def select_all(scores, points, pesq=None):
-    """The reference's three winners per (utterance, algorithm), by its sequential scan (vectorised over
-    utterances).  ``pesq[alg][u][i]`` may be injected (None entries = candidate skipped); otherwise PESQ is
-    0.0 (see speech_enhancement_comparison)."""
+    """HOST restatement of the selection (vectorised over utterances): the reference's three winners per
+    (utterance, algorithm) by its sequential scan.  The product path selects on the device
+    (:func:`select_winners_device`); this scan is its cross-check and serves callers that only hold host tables.
+    ``pesq[alg][u][i]`` may be injected (None / NaN = candidate skipped); without it the ``pesq`` / ``balance``
+    entries are marked unavailable (a constant PESQ would make them the first valid grid point / the STOI
+    winner - not something to write into result files)."""
     out = {}
     for name, sc in scores.items():
         valid = (sc["flags"] & 1) != 0
         snr = np.where((sc["flags"] & 4) != 0, np.inf, sc["snr"].astype(np.float64))
-        pq = None
-        if pesq is not None:
-            pq = np.array([[np.nan if v is None else float(v) for v in row] for row in pesq[name]], dtype=np.float64)
-        out[name] = select_best_batch(points[name], sc["stoi"].astype(np.float64), pq, snr, valid)
+        pq = _pesq_array(pesq[name]) if pesq is not None else None
+        sel = select_best_batch(points[name], sc["stoi"].astype(np.float64), pq, snr, valid)
+        if pq is None:
+            warnings.warn("selection without PESQ: only the 'stoi' winner is available", stacklevel=2)
+            sel = [_mark_pesq_unavailable(b) for b in sel]
+        out[name] = sel
     return out
 
 
-def sweep_dataset(clean, noisy, grids=DEFAULT_GRIDS, sr=16000, select=True, chunk_items=DEFAULT_CHUNK_ITEMS, engine_kwargs=None):
+def select_winners_device(engine, items, pesq=None):
+    """Enqueue ``cse_select_best`` for every algorithm's nominal device table: {alg: device ``cse_winner_t``
+    [U][3]}.  Nothing is synchronised."""
+    return {name: engine.select_device(buf, pl["n_points"], None if pesq is None else _pesq_array(pesq[name]))
+            for name, _pts, buf, pl in items}
+
+
+def selection_from_winners(points, winners, pesq_available):
+    """{alg: host winners [U, 3]} -> {alg: [per-utterance dict as grid.select_best returns]}."""
+    return {name: [best_from_winners(points[name], w[u], pesq_available) for u in range(w.shape[0])]
+            for name, w in winners.items()}
+
+
+PESQ_CHUNK_ITEMS = 592        # candidates per launch when their waveforms go to the host PESQ pool (2 x 114 MB in flight)
+
+
+def sweep_dataset(clean, noisy, grids=DEFAULT_GRIDS, sr=16000, select=True, chunk_items=DEFAULT_CHUNK_ITEMS,
+                  engine_kwargs=None, tables=True, pesq=None, pesq_scorer=None, pesq_workers=None):
     """clean, noisy: host arrays [U, L] (equal-length, 16 kHz, pair-aligned).
 
-    Returns ``{"scores", "points", "nominal", "unique", "selection", "engine"}``."""
-    eng = SweepEngine(clean, noisy, sr=sr, chunk_items=chunk_items, **(engine_kwargs or {}))
-    scores, points, unique = run_engine(eng, grids)
+    The device computes every candidate's scores AND the reference's three winners per (utterance, algorithm);
+    ``tables=False`` returns only the winners (48-byte records) instead of also copying the per-point score
+    tables (16 B x points x utterances) to the host.  ``pesq`` = {alg: [U][P]} host-side PESQ values for the
+    ``pesq`` / ``balance`` winners; or ``pesq_scorer(clean, wav, sr)`` (e.g. ``calculate_pesq``) to have every
+    candidate scored by a host process pool while the sweep runs (:mod:`.pesq_pool`; costs what PESQ costs).
+
+    Returns ``{"scores", "points", "nominal", "unique", "winners", "selection", "engine"}``."""
+    if pesq_scorer is not None:
+        if pesq is not None:
+            raise ValueError("give either a PESQ table or a scorer, not both")
+        eng = SweepEngine(clean, noisy, sr=sr, chunk_items=min(chunk_items, PESQ_CHUNK_ITEMS), **(engine_kwargs or {}))
+        items, pesq = run_engine_device_with_pesq(eng, pesq_scorer, grids, pesq_workers=pesq_workers)
+    else:
+        eng = SweepEngine(clean, noisy, sr=sr, chunk_items=chunk_items, **(engine_kwargs or {}))
+        items = run_engine_device(eng, grids)
+    points = {name: pts for name, pts, _, _ in items}
+    unique = sum(pl["unique"] for _, _, _, pl in items)
+    winners = selection = None
+    if select:
+        dev = select_winners_device(eng, items, pesq)
+        winners = {name: eng.winners_to_host(w, tag=(name, "winners")).copy() for name, w in dev.items()}
+        if pesq is None:
+            warnings.warn("selection without PESQ: only the 'stoi' winner is available", stacklevel=2)
+        selection = selection_from_winners(points, winners, pesq is not None)
+    scores = None
+    if tables:
+        scores = {name: eng.table_to_host(eng.be.view_bytes_as(buf, np.uint8, tag=(name, "table")), pl, eng.U)
+                  for name, _, buf, pl in items}
     nominal = sum(len(p) for p in points.values()) * eng.U
     return {"scores": scores, "points": points, "nominal": nominal, "unique": unique * eng.U,
-            "selection": select_all(scores, points) if select else None, "engine": eng}
+            "winners": winners, "selection": selection, "pesq": pesq, "engine": eng}
 
 
-def sweep_pairs(pairs, grids=DEFAULT_GRIDS, sr=16000, select=True, chunk_items=DEFAULT_CHUNK_ITEMS, engine_kwargs=None):
+def sweep_pairs(pairs, grids=DEFAULT_GRIDS, sr=16000, select=True, chunk_items=DEFAULT_CHUNK_ITEMS, engine_kwargs=None,
+                tables=True):
     """Variable-length form of :func:`sweep_dataset`: ``pairs`` is a list of (clean, noisy) 1-D arrays
     (each pair equal length, pair-aligned, 16 kHz).  Pairs are bucketed by length - one engine (and
     one set of cached spectrograms) per distinct length - and results are returned in input order."""
@@ -97,16 +185,24 @@ def sweep_pairs(pairs, grids=DEFAULT_GRIDS, sr=16000, select=True, chunk_items=D
         if c.ndim != 1 or c.shape != n.shape:
             raise ValueError(f"pair {i}: clean and noisy must be 1-D arrays of equal length")
         by_len.setdefault(len(c), []).append(i)
-    scores, points, nominal, unique = None, None, 0, 0
-    for L, idx in sorted(by_len.items()):
-        out = sweep_dataset(np.stack([pairs[i][0] for i in idx]), np.stack([pairs[i][1] for i in idx]), grids=grids,
-                            sr=sr, select=False, chunk_items=chunk_items, engine_kwargs=engine_kwargs)
-        if scores is None:
+    scores, winners, points, nominal, unique = None, None, None, 0, 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for L, idx in sorted(by_len.items()):
+            out = sweep_dataset(np.stack([pairs[i][0] for i in idx]), np.stack([pairs[i][1] for i in idx]), grids=grids,
+                                sr=sr, select=select, chunk_items=chunk_items, engine_kwargs=engine_kwargs, tables=tables)
             points = out["points"]
-            scores = {name: np.zeros((len(pairs), sc.shape[1]), dtype=sc.dtype) for name, sc in out["scores"].items()}
-        for name, sc in out["scores"].items():
-            scores[name][idx] = sc
-        nominal += out["nominal"]
-        unique += out["unique"]
-    return {"scores": scores, "points": points, "nominal": nominal, "unique": unique,
-            "selection": select_all(scores, points) if select else None}
+            if tables:
+                if scores is None:
+                    scores = {name: np.zeros((len(pairs), sc.shape[1]), dtype=sc.dtype) for name, sc in out["scores"].items()}
+                for name, sc in out["scores"].items():
+                    scores[name][idx] = sc
+            if select:
+                if winners is None:
+                    winners = {name: np.zeros((len(pairs), 3), dtype=w.dtype) for name, w in out["winners"].items()}
+                for name, w in out["winners"].items():
+                    winners[name][idx] = w
+            nominal += out["nominal"]
+            unique += out["unique"]
+    return {"scores": scores, "points": points, "nominal": nominal, "unique": unique, "winners": winners,
+            "selection": selection_from_winners(points, winners, False) if select else None}

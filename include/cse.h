@@ -160,6 +160,26 @@ int cse_stoi_items(const void* tables, const void* wav, int item0, int n_items, 
 int cse_expand_scores(const cse_score_t* unique_scores, const int* base, const int* stride,
                       int n_utts, int n_points, cse_score_t* out, void* stream);
 
+/* The three winners of optimize_parameters' sequential scan with hysteresis
+ * (Code/speech_enhancement_comparison.py:186-216): a candidate replaces the running best of a criterion
+ * only if it beats it by more than 1e-6 (stoi), 1e-3 (pesq), 1e-5 (balance), in grid order - an
+ * order-dependent scan, not an argmax.  table [n_utts][n_points] is a nominal score table (grid order);
+ * pesq [n_utts][n_points] doubles holds the host-side PESQ of every candidate (NaN = calculate_pesq
+ * returned None, candidate skipped, :180-181) or is NULL (PESQ = 0.0 for every candidate: only the
+ * `stoi` winner is then meaningful).  winners [n_utts][3] in the order stoi, pesq, balance; index -1 =
+ * no candidate qualified.  Comparisons are done in double on the table's values, exactly as the host
+ * scan (grid.select_best) does them. */
+typedef struct cse_winner_t {
+    int32_t index;      /* grid index of the winner, -1 if none */
+    int32_t lag;        /* its alignment lag (finalize_enhanced) */
+    int32_t flags;      /* its CSE_FLAG_* */
+    int32_t reserved;
+    double score;       /* the criterion's value */
+    double stoi, pesq, snr; /* the winner's other metrics (snr = +inf under CSE_FLAG_SNR_INF) */
+} cse_winner_t;
+int cse_select_best(const cse_score_t* table, const double* pesq, int n_utts, int n_points,
+                    cse_winner_t* winners, void* stream);
+
 /* Host-side probe used by the tests: evaluates the special-function fits the gain kernels
  * inline (which = 0: exp(-v/2)[(1+v)I0(v/2)+vI1(v/2)] of Code/mmse.py:92-96; 1: E1(v) of
  * Code/advanced_mmse.py:103) at x[0..n) in the library's precision. */

@@ -157,6 +157,7 @@ static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; 
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
 using std::isfinite; using std::isnan; using std::isinf; using std::min; using std::max;
 
 namespace cse_emu {

@@ -133,7 +133,7 @@ class NumpyBackend:
     def synchronize(self):
         pass
 
-    def view_bytes_as(self, buf, dtype):
+    def view_bytes_as(self, buf, dtype, tag=None):
         return buf.view(dtype)
 
 

@@ -27,9 +27,18 @@ def _worker(rank, world, port, q):
     use_emulated_runtime()
     dist.init_process_group("gloo", rank=rank, world_size=world)
     clean, noisy = make_batch(3, 9000)
-    out = sweep_sharded(clean, noisy, grids=GRID, select=True)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = sweep_sharded(clean, noisy, grids=GRID, select=True, tables=True)
+        lean = sweep_sharded(clean, noisy, grids=GRID, select=True)          # winners only: no table gather
+    assert lean["scores"] is None and np.array_equal(lean["winners"]["wiener"], out["winners"]["wiener"])
+    rng = np.random.default_rng(3)
+    pesq = {"wiener": np.round(rng.uniform(1, 3, (3, 4)), 2)}                 # host-side PESQ table of the whole dataset
+    withp = sweep_sharded(clean, noisy, grids=GRID, select=True, pesq=pesq)
     if rank == 0:
-        q.put((out["scores"]["wiener"], [b["stoi"]["index"] for b in out["selection"]["wiener"]]))
+        q.put((out["scores"]["wiener"], out["winners"]["wiener"], withp["winners"]["wiener"],
+               [b["stoi"]["index"] for b in out["selection"]["wiener"]]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -48,16 +57,33 @@ def test_two_rank_gloo_equals_single_process():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    scores, sel = q.get(timeout=240)
+    scores, winners, winners_pesq, sel = q.get(timeout=240)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     use_emulated_runtime()
     try:
         clean, noisy = make_batch(3, 9000)
-        single = sweep_dataset(clean, noisy, grids=GRID)
+        import warnings
+        from classical_speech_enhancement_b200.sweep import select_all
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            single = sweep_dataset(clean, noisy, grids=GRID)
+            host = select_all(single["scores"], single["points"])
+        rng = np.random.default_rng(3)
+        pesq = {"wiener": np.round(rng.uniform(1, 3, (3, 4)), 2)}
+        single_p = sweep_dataset(clean, noisy, grids=GRID, pesq=pesq)
+        host_p = select_all(single_p["scores"], single_p["points"], pesq=pesq)
     finally:
         use_product_runtime()
     assert np.array_equal(scores, single["scores"]["wiener"])
     assert sel == [b["stoi"]["index"] for b in single["selection"]["wiener"]]
+    # the winners gathered from the two ranks == the single-process device selection == the host scan
+    assert np.array_equal(winners, single["winners"]["wiener"]) and np.array_equal(winners_pesq, single_p["winners"]["wiener"])
+    assert single["selection"]["wiener"][0]["pesq"]["index"] is None          # no PESQ -> marked unavailable
+    for u in range(3):
+        assert single["selection"]["wiener"][u]["stoi"]["index"] == host["wiener"][u]["stoi"]["index"]
+        for c in ("stoi", "pesq", "balance"):
+            a, b = single_p["selection"]["wiener"][u][c], host_p["wiener"][u][c]
+            assert a["index"] == b["index"] and a["score"] == b["score"] and a["params"] == b["params"]
     assert single["nominal"] == 3 * 4 and single["unique"] == 3 * 4

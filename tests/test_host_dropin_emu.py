@@ -144,3 +144,68 @@ def test_sweep_pairs_buckets_by_length_and_result_files(tmp_path):
     assert lines[0].startswith("stem,alg,stoi_noisy") and lines[1].startswith("synth_000,wiener,")
     import json
     assert json.loads((tmp_path / "all_results.json").read_text())[0]["best_params_stoi"]["n_fft"] == 256
+
+
+def _fake_pesq(clean, deg, sr):          # deterministic stand-in, sensitive to the waveform
+    return 1.0 + 3.0 * float(np.clip(np.corrcoef(clean, deg)[0, 1], 0, 1))
+
+
+def test_optimize_parameters_accepts_the_reference_wrapper_closure_and_foreign_callables():
+    """The reference passes ``algorithm_wrapper`` - a closure around the entry point
+    (``speech_enhancement_comparison.py:282-294``) - not the entry point itself."""
+    import warnings
+    from classical_speech_enhancement_b200.speech_enhancement_comparison import _resolve_algorithm, optimize_parameters
+    from classical_speech_enhancement_b200.wiener_filter import wiener_filter
+    c, n = make_pair(5, 11000)
+    c, n = f32(c), f32(n)
+    alg_fn = wiener_filter
+
+    def algorithm_wrapper(noisy_audio, sr, **params):
+        if params.get("noise_method") == "true_noise":
+            return alg_fn(noisy_audio, sr, clean_audio=c, **params)
+        return alg_fn(noisy_audio, sr, **params)
+
+    assert _resolve_algorithm(algorithm_wrapper) == "wiener"
+    import functools
+    assert _resolve_algorithm(functools.partial(wiener_filter)) == "wiener"
+    ranges = dict(SMALL_WIENER, hop_length=[128], noise_percentile=[10.0], noise_method=["percentile", "true_noise"])
+    direct = optimize_parameters(c, n, 16000, wiener_filter, ranges, pesq_scorer=_fake_pesq, pesq_workers=0, verbose=False)
+    wrapped = optimize_parameters(c, n, 16000, algorithm_wrapper, ranges, pesq_scorer=_fake_pesq, pesq_workers=2, verbose=False)
+
+    def foreign(noisy_audio, sr, **params):            # nothing to unwrap: executed one grid point at a time
+        kw = {"clean_audio": c} if params["noise_method"] == "true_noise" else {}
+        return oracle.wiener_filter(noisy_audio, sr, **kw, **params)
+
+    assert _resolve_algorithm(foreign) is None
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        loop = optimize_parameters(c, n, 16000, foreign, ranges, pesq_scorer=_fake_pesq, pesq_workers=0, verbose=False)
+    assert any("one grid point at a time" in str(x.message) for x in w)
+    for crit in ("stoi", "pesq", "balance"):
+        assert wrapped[crit]["params"] == direct[crit]["params"] and wrapped[crit]["score"] == direct[crit]["score"]
+        assert loop[crit]["params"] == direct[crit]["params"] and abs(loop[crit]["score"] - direct[crit]["score"]) < 1e-5
+        assert np.abs(loop[crit]["enhanced"] - direct[crit]["enhanced"]).max() < 1e-5
+
+
+def test_dataset_sweep_with_pesq_pool_equals_oracle_selection():
+    """PESQ-complete selection (8f-1): every candidate's finalized waveform goes chunk-wise to a host process pool
+    (stand-in scorer) and the three winners equal ``oracle.sweep_one_pair(pesq_fn=...)`` for every utterance."""
+    from classical_speech_enhancement_b200.sweep import select_all, sweep_dataset
+    from classical_speech_enhancement_b200.synth import make_batch
+    clean, noisy = make_batch(2, 9000, first=30)
+    clean, noisy = f32(clean), f32(noisy)
+    ranges = {"alpha": [0.90, 0.98], "gain_floor": [0.01, 0.1], "n_fft": [256], "hop_length": [128],
+              "noise_percentile": [10.0, 20.0], "noise_method": ["percentile", "min_tracking"]}
+    out = sweep_dataset(clean, noisy, grids=(("wiener", ranges),), pesq_scorer=_fake_pesq, pesq_workers=2,
+                        chunk_items=5)
+    assert out["pesq"]["wiener"].shape == (2, 16) and not np.isnan(out["pesq"]["wiener"]).any()
+    host = select_all(out["scores"], out["points"], pesq=out["pesq"])
+    for u in range(2):
+        pts, scores, best = oracle.sweep_one_pair(clean[u], noisy[u], 16000, oracle.wiener_filter, ranges, pesq_fn=_fake_pesq)
+        assert np.abs(out["pesq"]["wiener"][u] - np.array([s["pesq"] for s in scores])).max() < 1e-4
+        for crit in ("stoi", "pesq", "balance"):
+            assert out["selection"]["wiener"][u][crit]["params"] == best[crit]["params"], (u, crit)
+            assert out["selection"]["wiener"][u][crit]["index"] == host["wiener"][u][crit]["index"]
+    # dead parameters: one PESQ evaluation serves both noise_percentile values under min_tracking
+    pq = out["pesq"]["wiener"][0].reshape(2, 2, 1, 1, 2, 2)
+    assert np.array_equal(pq[..., 0, 1], pq[..., 1, 1])
