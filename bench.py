@@ -134,48 +134,62 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------ CPU path (oracle port)
+_PAIRS = {}          # utterance id -> (clean, noisy) float64 of float32-rounded samples; filled BEFORE any timing / fork
+
+
+def _load_pairs(utts, L):
+    from classical_speech_enhancement_b200.synth import make_pair
+    for u in utts:
+        if u not in _PAIRS:
+            c, n = make_pair(u, L)
+            _PAIRS[u] = (c.astype(np.float32).astype(np.float64), n.astype(np.float32).astype(np.float64))
+
+
 def _cpu_task(task):
-    """One utterance-config through the reference's per-candidate procedure (no caching), no PESQ."""
+    """One utterance-config through the reference's per-candidate procedure (no caching), no PESQ.  The synthetic
+    pair comes from the pre-generated cache: data generation is NOT part of the timed work."""
     import oracle
     from oracle.search import score_candidate
-    from classical_speech_enhancement_b200.synth import make_pair
     alg, point, u, L = task
-    c, n = make_pair(u, L)
-    c = c.astype(np.float32).astype(np.float64)
-    n = n.astype(np.float32).astype(np.float64)
+    c, n = _PAIRS[u]
     t = time.perf_counter()
-    fn = oracle.ALGORITHMS[alg]
-    enh = fn(n, SR, **point)
+    enh = oracle.ALGORITHMS[alg](n, SR, **point)
     sc = score_candidate(c, enh, SR)
-    return time.perf_counter() - t, (sc["stoi"] if sc else None)
+    return time.perf_counter() - t, (sc["stoi"] if sc else None), (sc["snr"] if sc else None)
 
 
-def cpu_sample(n_tasks, L, seed=0):
-    """Random (algorithm, grid point, utterance) triples drawn uniformly from the nominal 9744-point grid."""
+def cpu_sample(n_tasks, L, seed=0, n_utts=824):
+    """Random (algorithm, grid point index, utterance) triples drawn uniformly from the nominal 9744-point grid."""
     from classical_speech_enhancement_b200.grid import grid_points
     from classical_speech_enhancement_b200.sweep import DEFAULT_GRIDS
-    allpts = [(name, p) for name, ranges in DEFAULT_GRIDS for p in grid_points(ranges)]
+    allpts = [(name, i, p) for name, ranges in DEFAULT_GRIDS for i, p in enumerate(grid_points(ranges))]
     rng = np.random.default_rng(seed)
     idx = rng.choice(len(allpts), n_tasks, replace=False)
-    return [(allpts[i][0], allpts[i][1], int(rng.integers(0, 824)), L) for i in idx]
+    return [(allpts[i][0], allpts[i][1], allpts[i][2], int(rng.integers(0, n_utts)), L) for i in idx]
 
 
-def cpu_baseline_single_thread(L, n_tasks=160):
+def cpu_baseline_single_thread(L, n_tasks=160, n_utts=824):
+    """-> (cpu_baseline dict, [(alg, point index, utterance, stoi, snr)] of the sample for the parity check)."""
     for v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
         os.environ.setdefault(v, "1")
-    tasks = cpu_sample(n_tasks, L, seed=0)
-    t = time.perf_counter()
-    for task in tasks:
-        _cpu_task(task)
-    dt = time.perf_counter() - t
-    return {"value": n_tasks / dt, "unit": UNIT, "cores": 1, "kind": "port",
-            "sample": f"{n_tasks} random (algorithm, grid point, utterance) configs of the {L}-sample workload, "
-                      f"seed 0, fp64 numpy/scipy oracle, no cross-candidate caching, no PESQ, {dt:.1f} s"}
+    tasks = cpu_sample(n_tasks, L, seed=0, n_utts=n_utts)
+    _load_pairs({t[3] for t in tasks}, L)                      # untimed
+    dt, sample = 0.0, []
+    for alg, i, point, u, _ in tasks:
+        d, stoi, snr = _cpu_task((alg, point, u, L))
+        dt += d
+        sample.append((alg, i, u, stoi, snr))
+    return ({"value": n_tasks / dt, "unit": UNIT, "cores": 1, "kind": "port",
+             "sample": f"{n_tasks} random (algorithm, grid point, utterance) configs of the {L}-sample workload, "
+                       f"seed 0, fp64 numpy/scipy oracle, no cross-candidate caching, no PESQ, {dt:.1f} s of oracle "
+                       "time (synthetic-pair generation excluded)"}, sample)
 
 
 def run_reference_arm(args):
     """--impl reference: the reference's CPU implementation of the path.  The reference itself cannot be
-    imported (librosa/pystoi/pesq absent), so this is the oracle port, on all host cores."""
+    imported (librosa/pystoi/pesq absent), so this is the oracle port, on all host cores.  Each step is a bounded
+    random sample of the C5 workload (the CPU never executes all 8 M configs); the synthetic pairs are generated
+    before the pool forks, outside every timed region."""
     import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -186,10 +200,14 @@ def run_reference_arm(args):
     per_step = max(64, 4 * cores)
     L = args.length
     mean_bytes, nominal = grid_mean_bytes(L)
+    from classical_speech_enhancement_b200.sweep import nominal_and_unique
+    unique_points = nominal_and_unique()[1]         # a property of the grid (dead parameters), identical in both arms' config
+    steps = [[(a, p, u, L) for a, _i, p, u, _ in cpu_sample(per_step, L, seed=step, n_utts=args.utts)]
+             for step in range(args.warmup + args.steps)]
+    _load_pairs({t[2] for st in steps for t in st}, L)
     with mp.get_context("fork").Pool(cores) as pool:
         times = []
-        for step in range(args.warmup + args.steps):
-            tasks = cpu_sample(per_step, L, seed=step)
+        for step, tasks in enumerate(steps):
             t = time.perf_counter()
             pool.map(_cpu_task, tasks, chunksize=1)
             dt = time.perf_counter() - t
@@ -201,12 +219,15 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, nominal, None),
+        "config": workload_config(args, nominal, unique_points),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{per_step} random configs of the workload per step on {cores} processes "
-                                   "(fp64 numpy/scipy oracle restatement of the reference; PESQ excluded)"},
+                                   "(fp64 numpy/scipy oracle restatement of the reference; PESQ excluded; every config "
+                                   "recomputes its STFT / noise PSD as the reference does; data generation untimed)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "configs/s of NOMINAL grid points (the CPU path never dedupes dead parameters); extrapolates a sampled "
+                "subset, the full C5 step would take ~" + f"{nominal * args.utts / value / 3600:.0f} h on this host",
     }
     print(json.dumps(line), flush=True)
 
@@ -214,12 +235,13 @@ def run_reference_arm(args):
 def workload_config(args, nominal_points, unique_points):
     return {"workload": f"C5: all four algorithms x full parameter_ranges.py grid ({nominal_points} nominal grid "
                         f"points/utterance) x {args.utts} synthetic 16 kHz pairs of {args.length} samples, "
-                        "enhance + finalize + STOI + SNR per candidate (PESQ excluded, host-side)",
+                        "enhance + finalize + STOI + SNR per candidate + the three-way selection scan per (utterance, "
+                        "algorithm) (PESQ excluded, host-side)",
             "utterances": args.utts, "length": args.length, "grid_points_nominal": nominal_points,
             "grid_points_unique": unique_points, "chunk_items": args.chunk,
             "cache_hygiene": "inputs larger than L2: waveforms + spectrogram / noise-PSD caches of the shard are "
                              "GBs and every step recomputes them from the raw signals; candidate waveforms are "
-                             "rewritten every chunk; score tables return through recycled pinned staging buffers",
+                             "rewritten every chunk; winners return through recycled pinned staging buffers",
             "parallelism": f"utterance-sharded x{args.gpus}"}
 
 
@@ -272,14 +294,20 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident arm: inputs already in HBM
+    from classical_speech_enhancement_b200.distributed import gather_winners
+    import warnings
+    warnings.filterwarnings("ignore", message="selection without PESQ")
     eng = SweepEngine(clean_pin.numpy(), noisy_pin.numpy(), chunk_items=args.chunk)
 
     u_pad = max(b[r + 1] - b[r] for r in range(world))
 
-    def step_resident():
-        eng.reset()
-        items = sw.run_engine_device(eng, u_pad=u_pad)
-        return gather_device_scores(eng, items, args.utts, device=device)   # NCCL all_gather (N>1) + D2H + expansion
+    def step_resident(e=None):
+        """The whole path: caches dropped, STFTs / noise PSDs / clean caches / sweep of all four grids, the
+        selection scan on this rank's device, ONE all_gather of the winners' records (N>1), winners to the host."""
+        e = e or eng
+        e.reset()
+        items = sw.run_engine_device(e, u_pad=u_pad)
+        return items, gather_winners(e, sw.select_winners_device(e, items), args.utts, u_pad)
 
     sampler = ClockSampler(range(world) if rank == 0 else [])
     sampler.start()
@@ -293,7 +321,7 @@ def main():
     t0 = time.perf_counter()
     ev0.record()
     for _ in range(args.steps):
-        scores = step_resident()
+        items, winners = step_resident()
     ev1.record()
     barrier()
     wall = time.perf_counter() - t0
@@ -311,30 +339,84 @@ def main():
     dev_s, wall_s = float(t[0]), float(t[1])
     step_s = max(dev_s, 1e-9) / args.steps
 
-    # ---------------- end-to-end arm: host buffers in, host score tables out, every step
-    def step_e2e():
-        # host buffers in (pinned), host score tables out: the public dataset-level path
-        e = SweepEngine(clean_pin.numpy(), noisy_pin.numpy(), chunk_items=args.chunk)
-        items = sw.run_engine_device(e, u_pad=u_pad)
-        return e, gather_device_scores(e, items, args.utts, device=device)
+    # ---------------- untimed: the full per-point tables of the last step (parity check, checksum across N)
+    import hashlib
+    scores = gather_device_scores(eng, items, args.utts, device=device)
+    names = [name for name, _r in sw.DEFAULT_GRIDS]
+    sha = hashlib.sha256()
+    for name in names:
+        sha.update(np.ascontiguousarray(scores[name]).view(np.uint8).reshape(-1).data)
+    score_sha256 = sha.hexdigest()
+    wsha = hashlib.sha256()
+    for name in names:
+        wsha.update(np.ascontiguousarray(winners[name]).view(np.uint8).reshape(-1).data)
+    # the device selection against the host restatement of the reference's scan, over the whole job
+    host_sel = sw.select_all(scores, {name: pts for name, pts, _, _ in items}) if rank == 0 else None
+    sel_mismatch = None
+    if rank == 0:
+        sel_mismatch = sum(int(host_sel[name][u]["stoi"]["index"] != (int(winners[name][u, 0]["index"]) if winners[name][u, 0]["index"] >= 0 else None))
+                           for name in names for u in range(args.utts))
+    table_for_parity = {name: scores[name].copy() for name in names} if rank == 0 else None
+    del scores
 
-    del eng
+    # ---------------- end-to-end arm: host buffers in, winners out, every step
+    def step_e2e():
+        # the public dataset-level path (sweep.sweep_dataset / distributed.sweep_sharded with tables=False):
+        # pinned host waveforms -> device, whole sweep, device selection, winners -> host
+        e = SweepEngine(clean_pin.numpy(), noisy_pin.numpy(), chunk_items=args.chunk)
+        its = sw.run_engine_device(e, u_pad=u_pad)
+        return e, gather_winners(e, sw.select_winners_device(e, its), args.utts, u_pad)
+
+    def step_e2e_tables():
+        # same + the full per-point score tables gathered to every rank's host (what round 1 reported as e2e)
+        e = SweepEngine(clean_pin.numpy(), noisy_pin.numpy(), chunk_items=args.chunk)
+        its = sw.run_engine_device(e, u_pad=u_pad)
+        w = gather_winners(e, sw.select_winners_device(e, its), args.utts, u_pad)
+        return e, (w, gather_device_scores(e, its, args.utts, device=device))
+
+    del eng, items
     torch.cuda.empty_cache()
-    step_e2e()
-    barrier()
-    e2e_steps = max(1, min(args.steps, 2))
-    t0 = time.perf_counter()
-    e2e_eng = e2e_scores = None
-    for _ in range(e2e_steps):
-        e2e_eng = None                   # the previous step's engine returns its buffers to the caching allocator first
-        e2e_eng, e2e_scores = step_e2e()
-    barrier()
-    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te[0]) / e2e_steps
-    h2d = e2e_eng.h2d_bytes
-    d2h = args.utts * nominal_points * e2e_eng.lib.score_dtype.itemsize    # the (gathered) nominal score tables, per rank
+
+    def time_e2e(fn):
+        fn()
+        barrier()
+        n = max(1, min(args.steps, 2))
+        t0 = time.perf_counter()
+        e = None
+        for _ in range(n):
+            e = None                     # the previous step's engine returns its buffers to the caching allocator first
+            e, _out = fn()
+        barrier()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        h2d = e.h2d_bytes
+        del e
+        torch.cuda.empty_cache()
+        return float(te[0]) / n, h2d
+
+    e2e_s, h2d = time_e2e(step_e2e)
+    e2e_tab_s, _ = time_e2e(step_e2e_tables)
+    from classical_speech_enhancement_b200._lib import WINNER_DTYPE
+    d2h = args.utts * len(names) * 3 * WINNER_DTYPE.itemsize                 # the (gathered) winners, per rank
+    d2h_tables = d2h + args.utts * nominal_points * 16
+
+    # ---------------- config 1 latency: one spectral-subtraction call through the drop-in entry point
+    c1 = None
+    if rank == 0:
+        from classical_speech_enhancement_b200.spectral_subtractor import spectral_subtraction
+        c1n, c1c = noisy_h[0].astype(np.float64), clean_h[0].astype(np.float64)
+        kw = dict(alpha=2.0, beta=0.01, n_fft=512, hop_length=128, noise_percentile=10.0, noise_method="true_noise",
+                  clean_audio=c1c)
+        for _ in range(3):
+            spectral_subtraction(c1n, SR, **kw)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            spectral_subtraction(c1n, SR, **kw)
+        c1 = {"workload": "C1: spectral_subtraction(noisy, 16000, n_fft=512, hop=128, true_noise), one 3 s pair, host "
+                          "array in -> host float64 waveform out (H2D, STFT, oracle noise PSD, gain + ISTFT, D2H)",
+              "ms_per_call": 1e3 * (time.perf_counter() - t0) / 20}
 
     # ---------------- roofline of the dominant kernel (events around every chunk launch, timed steps only)
     names = {0: "ss", 1: "wiener", 2: "mmse", 3: "omlsa"}
@@ -352,6 +434,8 @@ def main():
                  else ("stoi_stream_kernel" if kind == "stoi" else "align_kernel<0>"))
         t = tags.setdefault(kname, [0.0, 0.0, 0, per])
         t[0] += by; t[1] += ms; t[2] += items
+    exec_items = sum(v[2] for k, v in fam.items() if k == "enhance")
+    exec_bytes = sum(v[0] for k, v in fam.items() if k in ("enhance", "stoi"))
     peaks, traffic_tab = {}, {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -391,13 +475,24 @@ def main():
                                    "achieved": total_configs / step_s * mean_bytes / 1e9 / world,
                                    "frac": total_configs / step_s * mean_bytes / 1e9 / world / peak,
                                    "note": "per GPU; nominal configs x grid-mean algorithmic bytes (SURVEY 8d)"},
+                    "whole_path_executed": {"bytes_per_config": exec_bytes / max(1, exec_items),
+                                            "achieved": exec_bytes / args.steps / step_s / 1e9,
+                                            "frac": exec_bytes / args.steps / step_s / 1e9 / peak,
+                                            "note": "per GPU (this rank); only the candidates the kernels executed "
+                                                    "(dead-parameter duplicates are broadcast, not computed) x their own bytes"},
                     "note": "instruction-issue-bound kernels (see DESIGN.md section 6): DRAM traffic is far below the "
                             "algorithmic bytes because Y / noise PSD are shared by all candidates of an utterance and hit in L2"}
 
     if rank == 0:
-        cpu = None
+        cpu, parity = None, None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_baseline_single_thread(L)
+            cpu, sample = cpu_baseline_single_thread(L, n_utts=args.utts)
+            ds = [abs(float(table_for_parity[a][u, i]["stoi"]) - st) for a, i, u, st, _ in sample if st is not None]
+            dn = [abs(float(table_for_parity[a][u, i]["snr"]) - sn) for a, i, u, _, sn in sample if sn is not None and np.isfinite(sn)]
+            bad = sum(1 for a, i, u, st, _ in sample if (st is None) != (not table_for_parity[a][u, i]["flags"] & 1))
+            parity = {"n": len(ds), "max_abs_dstoi": max(ds), "max_abs_dsnr_db": max(dn), "validity_mismatches": bad,
+                      "tolerance": {"stoi": 1e-4, "snr_db": 1e-3},
+                      "what": "device score-table entries of the timed job vs the fp64 oracle on the cpu_baseline sample"}
         line = {
             "metric": METRIC, "value": total_configs / step_s, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * step_s, "higher_is_better": True, "scaling": "strong",
@@ -405,8 +500,15 @@ def main():
             "config": workload_config(args, nominal_points, unique_points),
             "unique_value": args.utts * unique_points / step_s,
             "e2e": {"value": total_configs / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
+                    "what": "host waveforms in -> the three winners per (utterance, algorithm) out (device selection)"},
+            "e2e_with_tables": {"value": total_configs / e2e_tab_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                                "d2h_bytes_per_step": int(d2h_tables), "ms_per_step": 1e3 * e2e_tab_s,
+                                "what": "same + every candidate's score record gathered to every rank's host"},
             "gpu_launches": int(launches), "wall_ms_per_step": 1e3 * wall_s / args.steps,
+            "score_sha256": score_sha256, "winners_sha256": wsha.hexdigest(),
+            "selection_check": {"utterance_algorithms": args.utts * len(names), "device_vs_host_scan_mismatches": sel_mismatch},
+            "parity_check": parity, "c1_latency": c1,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -12,6 +12,7 @@ import numpy as np
 PKG = os.path.dirname(os.path.abspath(__file__))
 
 CSE_OK = 0
+CSE_EINVAL, CSE_ECUDA, CSE_EUNSUPPORTED, CSE_EWORKSPACE = -1, -2, -3, -4
 ALG_SS, ALG_WIENER, ALG_MMSE, ALG_OMLSA = 0, 1, 2, 3
 FLAG_VALID, FLAG_ALIGNED, FLAG_SNR_INF, FLAG_STOI_SHORT = 1, 2, 4, 8
 
@@ -25,6 +26,7 @@ SIGNATURES = {
     "cse_abi_version": (_i, []),
     "cse_dtype": (_i, []),
     "cse_last_error": (ctypes.c_char_p, []),
+    "cse_max_score_length": (_i, [_i]),
     "cse_bins_padded": (_i, [_i]),
     "cse_num_frames": (_i, [_i, _i]),
     "cse_tables_bytes": (_sz, []),
@@ -101,7 +103,7 @@ class CseLibrary:
         if sym not in SIGNATURES:
             raise AttributeError(name)
         fn = getattr(self._dll, sym)
-        if SIGNATURES[sym][0] is not _i or name in ("abi_version", "dtype", "bins_padded", "num_frames"):
+        if SIGNATURES[sym][0] is not _i or name in ("abi_version", "dtype", "bins_padded", "num_frames", "max_score_length"):
             return fn
 
         def call(*args):

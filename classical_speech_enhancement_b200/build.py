@@ -52,7 +52,7 @@ def build_cuda(fp64=False, force=False, verbose=False):
     if not force and not _stale(target):
         return target
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "--use_fast_math" if False else "-DCSE_NO_FAST_MATH", "-Xptxas", "-v",
+           "-DCSE_NO_FAST_MATH", "-Xptxas", "-v",
            "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include")]
     if fp64:
         cmd.append("-DCSE_FP64")

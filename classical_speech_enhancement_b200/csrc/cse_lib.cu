@@ -27,6 +27,17 @@ static int check_launch(const char* what) {
     if (e != cudaSuccess) return fail(CSE_ECUDA, "%s: %s", what, cudaGetErrorString(e));
     return CSE_OK;
 }
+// Opt-in to > 48 KB of dynamic shared memory once per (kernel instantiation, device) instead of on every launch.
+#define CSE_SMEM_OPT_IN(kfn, bytes)                                                                        \
+    do {                                                                                                    \
+        static unsigned long long cse_done_[2] = {0, 0};                                                    \
+        int cse_dev_ = 0;                                                                                   \
+        cudaGetDevice(&cse_dev_);                                                                           \
+        if ((size_t)(bytes) > 48 * 1024 && !((cse_done_[(cse_dev_ >> 6) & 1] >> (cse_dev_ & 63)) & 1ull)) { \
+            cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes));           \
+            cse_done_[(cse_dev_ >> 6) & 1] |= 1ull << (cse_dev_ & 63);                                       \
+        }                                                                                                   \
+    } while (0)
 static bool valid_nfft(int n_fft) { return n_fft == 256 || n_fft == 512 || n_fft == 1024 || n_fft == 2048; }
 #define CSE_REQUIRE(cond, ...) do { if (!(cond)) return fail(CSE_EINVAL, __VA_ARGS__); } while (0)
 
@@ -77,7 +88,7 @@ static int launch_stft(const CseTables* T, const real* wav, const real* minus, i
     constexpr int M = (1 << LOG2N) / 2;
     const size_t smem = (size_t)F * CSE_FFT_STRIDE(M) * sizeof(real2);
     auto kfn = stft_psd_kernel<LOG2N, F>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    CSE_SMEM_OPT_IN(kfn, smem);
     dim3 grid((nf + F - 1) / F, U);
     CSE_LAUNCH(kfn, grid, 256, smem, stream, T, wav, minus, L, hop, nf, floor_, Y, P);
     return check_launch("stft_psd_kernel");
@@ -109,7 +120,9 @@ static int launch_enhance(const EnhanceArgs& a, int n_items, void* stream) {
     const size_t smem = (size_t)(C::F * C::XST + 1) * sizeof(real2) + (size_t)(W + a.hop + 16) * sizeof(real) + (size_t)(C::M + FftTwLayout<LOG2N - 1, true>::SIZE) * sizeof(real2) +
                         (size_t)C::KMAX * ((C::F + 1) / 2) * C::NT * 2 * sizeof(unsigned) + (size_t)2 * C::NT * sizeof(real2);
     auto kfn = enhance_kernel<ALG, LOG2N>;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int hop_max = C::NFFT / 2;                                  // the opt-in covers every hop this instantiation accepts
+    const size_t smem_max = smem + (size_t)((C::F - 1) * (hop_max - a.hop) + (hop_max - a.hop)) * sizeof(real);
+    CSE_SMEM_OPT_IN(kfn, smem_max);
     CSE_LAUNCH(kfn, n_items, C::NT, smem, stream, a);
     return check_launch("enhance_kernel");
 }

@@ -91,6 +91,15 @@ static int check_sr(int sr) {
 }
 #define CSE_MAX_SMEM (227 * 1024)
 
+extern "C" int cse_max_score_length(int sr) {
+    if (sr != CSE_SR) return 0;
+    int lo = 1, hi = 1 << 24;                      // stoi_smem grows monotonically with the length
+    while (lo < hi) {
+        const int mid = lo + (hi - lo + 1) / 2;
+        if (stoi_smem(score_geom(mid)) <= CSE_MAX_SMEM) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
 extern "C" size_t cse_clean_cache_bytes(int length, int sr) { (void)sr; return length > 0 ? score_geom(length).bytes : 0; }
 extern "C" size_t cse_clean_workspace_bytes(int n_utts, int length, int sr) {
     (void)sr;
@@ -113,7 +122,7 @@ extern "C" int cse_prepare_clean(const void* tables, const void* clean, int n_ut
     double* y10d = (double*)workspace;
     double* energies = (double*)((unsigned char*)workspace + up64((size_t)n_utts * a.g.n10 * sizeof(double)));
     auto ka = align_kernel<true>;
-    cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)align_smem());
+    CSE_SMEM_OPT_IN(ka, align_smem());
     CSE_LAUNCH(ka, n_utts, 512, align_smem(), stream, a);
     const size_t vsm = (size_t)(8 * (CSE_RS_A + 17) + 40) * sizeof(double);
     CSE_LAUNCH(clean_vad_kernel, n_utts, 256, vsm, stream, a, y10d, energies);
@@ -146,12 +155,12 @@ static int score_items(const void* tables, const void* wav, int item0, int n_ite
     a.lagflags = (int*)((unsigned char*)workspace + up64((size_t)n_items * score_row_reals(a.g.nfrm) * sizeof(real)));
     if (which & 1) {
         auto ka = align_kernel<false>;
-        cudaFuncSetAttribute(ka, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)align_smem());
+        CSE_SMEM_OPT_IN(ka, align_smem());
         CSE_LAUNCH(ka, n_items, 512, align_smem(), stream, a);
     }
     if (which & 2) {
         auto ks = stoi_stream_kernel;
-        cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stoi_stream_smem());
+        CSE_SMEM_OPT_IN(ks, stoi_stream_smem());
         CSE_LAUNCH(ks, n_items, 256, stoi_stream_smem(), stream, a);
     }
     return check_launch("score");

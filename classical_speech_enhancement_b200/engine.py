@@ -13,6 +13,7 @@ suite, on numpy arrays against the thread-emulated kernels.  There is no CPU com
 the product: constructing :class:`SweepEngine` without a CUDA device raises.
 """
 import ctypes
+from collections import OrderedDict
 
 import numpy as np
 
@@ -29,8 +30,26 @@ MAX_WAV_WORKSPACE_BYTES = 8 << 30
 #: changes it (-> libcse_sm100a.so + CUDA tensors); the CPU test-suite points it at the
 #: thread-emulated build to exercise the host logic without a GPU.
 _runtime = {"lib": None, "backend_factory": None, "reuse_result_buffers": False}
-_PLAN_CACHE = {}
+_PLAN_CACHE = OrderedDict()      # (algorithm, grid digest, frame-count signature) -> host-side launch plan, LRU
+_PLAN_CACHE_MAX = 32
 _PINNED_POOL = {}
+_TABLES_CACHE = {}               # (library, device) -> constant tables buffer (twiddles, windows, resampler taps)
+
+
+class GridPoints(list):
+    """A grid's point list that remembers its content digest (see :func:`points_digest`); what
+    ``sweep.cached_points`` hands out so that repeated sweeps of the same grid skip re-hashing it."""
+    __slots__ = ("_cse_digest",)
+
+
+def points_digest(points):
+    """Content hash of a grid (order-sensitive: the selection scan depends on the order)."""
+    d = getattr(points, "_cse_digest", None)
+    if d is None:
+        d = hash(tuple(tuple(p.items()) for p in points))
+        if isinstance(points, GridPoints):
+            points._cse_digest = d
+    return d
 
 
 def configure_runtime(lib=None, backend_factory=None, reuse_result_buffers=None):
@@ -167,10 +186,18 @@ class SweepEngine:
         if clean.shape != noisy.shape or clean.ndim != 2:
             raise ValueError("clean and noisy must both be [U, L]")
         self.U, self.L = clean.shape
+        if self.has_clean and prepare_scoring and self.L > self.lib.max_score_length(sr):
+            raise _lib.CseError(_lib.CSE_EUNSUPPORTED, f"utterances of {self.L} samples exceed the scoring kernels' limit of "
+                                f"{self.lib.max_score_length(sr)} samples (about 38 s at 16 kHz); split the recording")
         self.chunk_items = max(1, min(int(chunk_items), MAX_WAV_WORKSPACE_BYTES // max(1, self.L * np.dtype(self.real).itemsize)))
         be, lib_ = self.be, self.lib
-        self.tables = be.empty((lib_.tables_bytes(),), np.uint8)
-        lib_.tables_init(be.ptr(self.tables), be.stream())
+        tkey = (id(lib_), getattr(be, "device", "host").__str__())
+        self.tables = _TABLES_CACHE.get(tkey)
+        if self.tables is None:        # constant tables: uploaded once per (library, device), shared by every engine
+            self.tables = be.empty((lib_.tables_bytes(),), np.uint8)
+            lib_.tables_init(be.ptr(self.tables), be.stream())
+            be.synchronize()
+            _TABLES_CACHE[tkey] = self.tables
         self.clean_host = np.ascontiguousarray(clean, dtype=self.real)      # kept for the host-side PESQ pool
         self.clean = be.from_host(self.clean_host)
         self.noisy = be.from_host(np.ascontiguousarray(noisy, dtype=self.real))
@@ -306,30 +333,58 @@ class SweepEngine:
 
     # ------------------------------------------------------------------ the sweep
     def _plan(self, alg, points):
-        """Grouped / deduplicated launch plan of a grid, cached per (algorithm, points list, length):
-        host-only data shared by every engine of the process; device-side maps are per engine."""
-        key = (alg, id(points), len(points), self.L)
-        hit = _PLAN_CACHE.get(key)
-        if hit is not None and hit[0] is points:
-            pl = self._plans.get(key)
-            if pl is None:
-                pl = dict(hit[1])
-                self._plans[key] = pl
+        """Grouped / deduplicated launch plan of a grid.  The host-side part is shared by every engine of the
+        process through a bounded LRU keyed by the grid's CONTENT (algorithm, digest of the points, which shapes
+        are time-varying) - never by object identity, so a rebuilt or edited point list can neither leak nor hit
+        a stale plan; device-side maps / parameter uploads live in the per-engine copy."""
+        sig = tuple(sorted({(int(p["n_fft"]), int(p["hop_length"]), self.n_frames(int(p["n_fft"]), int(p["hop_length"])) >= 5)
+                            for p in points}))
+        self._validate_shapes(points)
+        key = (alg, points_digest(points), len(points), sig)
+        pl = self._plans.get(key)
+        if pl is not None:
             return pl
-        groups = plan(alg, points, self.n_frames)
-        info, col = [], 0
-        for gkey, g in groups.items():
-            n_rows = len(g["rows"])
-            member_idx = np.concatenate([np.asarray(m, dtype=np.int64) for m in g["members"]])
-            row_idx = np.concatenate([np.full(len(m), r, dtype=np.int64) for r, m in enumerate(g["members"])])
-            info.append({"key": gkey, "rows": g["rows"], "params_host": _lib.pack_params(g["rows"]), "n_rows": n_rows,
-                         "col0": col, "member_idx": member_idx, "row_idx": row_idx, "members": g["members"]})
-            col += n_rows
-        out = {"groups": info, "unique": col, "n_points": len(points)}
-        _PLAN_CACHE[key] = (points, out)
+        out = _PLAN_CACHE.get(key)
+        if out is not None:
+            _PLAN_CACHE.move_to_end(key)
+        else:
+            groups = plan(alg, points, self.n_frames)
+            info, col = [], 0
+            for gkey, g in groups.items():
+                n_rows = len(g["rows"])
+                member_idx = np.concatenate([np.asarray(m, dtype=np.int64) for m in g["members"]])
+                row_idx = np.concatenate([np.full(len(m), r, dtype=np.int64) for r, m in enumerate(g["members"])])
+                info.append({"key": gkey, "rows": g["rows"], "params_host": _lib.pack_params(g["rows"]), "n_rows": n_rows,
+                             "col0": col, "member_idx": member_idx, "row_idx": row_idx, "members": g["members"]})
+                col += n_rows
+            out = {"groups": info, "unique": col, "n_points": len(points)}
+            _PLAN_CACHE[key] = out
+            while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
+                _PLAN_CACHE.popitem(last=False)
         pl = dict(out)
         self._plans[key] = pl
         return pl
+
+    def _validate_shapes(self, points):
+        """The build's operating range (include/cse.h), checked once per grid with a message that names the
+        offending point instead of failing in the middle of a sweep."""
+        seen = set()
+        for p in points:
+            k = (int(p["n_fft"]), int(p["hop_length"]), p.get("noise_method"))
+            if k in seen:
+                continue
+            seen.add(k)
+            n_fft, hop, method = k
+            if n_fft not in (256, 512, 1024, 2048):
+                raise _lib.CseError(_lib.CSE_EINVAL, f"n_fft {n_fft} not in {{256,512,1024,2048}}")
+            if hop <= 0 or hop % 2 or hop > n_fft // 2:
+                raise _lib.CseError(_lib.CSE_EINVAL, f"hop {hop} must be even and <= n_fft/2 = {n_fft // 2}")
+            if self.L <= n_fft // 2:
+                raise _lib.CseError(_lib.CSE_EINVAL, f"length {self.L} must exceed n_fft/2 = {n_fft // 2} (reflect padding)")
+            nf = self.n_frames(n_fft, hop)
+            limit = 4096 if (method == "min_tracking" and nf >= 5) else (8192 if method in ("percentile", "min_tracking") else None)
+            if limit is not None and nf > limit:
+                raise _lib.CseError(_lib.CSE_EUNSUPPORTED, f"{nf} frames (hop {hop}) exceed the {method} estimator's limit of {limit}")
 
     def sweep_device(self, alg_name, points, u_pad=None, chunk_sink=None):
         """Enqueue the whole sweep of one algorithm; returns (device table, plan).

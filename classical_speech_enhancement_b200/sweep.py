@@ -9,7 +9,7 @@ import warnings
 
 import numpy as np
 
-from .engine import DEFAULT_CHUNK_ITEMS, SweepEngine
+from .engine import DEFAULT_CHUNK_ITEMS, GridPoints, SweepEngine
 from .grid import best_from_winners, grid_points, select_best_batch
 from .parameter_ranges import (param_ranges_mmse, param_ranges_omlsa, param_ranges_ss,
                                param_ranges_wiener)
@@ -36,10 +36,14 @@ def cached_points(name, ranges):
     """grid_points(ranges), cached per (algorithm, ranges object) so that engines can reuse their launch plans."""
     key = (name, id(ranges))
     hit = _points_cache.get(key)
-    if hit is None or hit[0] is not ranges:
-        hit = (ranges, grid_points(ranges))
+    if hit is None or hit[0] is not ranges or hit[2] != _ranges_signature(ranges):
+        hit = (ranges, GridPoints(grid_points(ranges)), _ranges_signature(ranges))
         _points_cache[key] = hit
     return hit[1]
+
+
+def _ranges_signature(ranges):
+    return tuple((k, tuple(v)) for k, v in ranges.items())
 
 
 def run_engine_device(engine, grids=DEFAULT_GRIDS, u_pad=None):

@@ -75,6 +75,15 @@ typedef struct cse_score_t { float stoi; float snr; int32_t lag; int32_t flags; 
 int cse_abi_version(void);
 int cse_dtype(void);                    /* 32 or 64 */
 const char* cse_last_error(void);
+/* Operating range of this build (checked by every entry point, CSE_EUNSUPPORTED / CSE_EINVAL otherwise;
+ * the reference itself has no such limits):
+ *   n_fft in {256, 512, 1024, 2048}; win_length = n_fft, periodic Hann, center=True, reflect padding;
+ *   hop even, 0 < hop <= n_fft/2 (the overlap-add kernel owns sample pairs); length > n_fft/2;
+ *   cse_noise_percentile: n_frames <= 8192;  cse_noise_mintrack: 5 <= n_frames <= 4096
+ *     (about 65 s / 32 s of audio at hop 128; the per-bin series is sorted / scanned in one CTA);
+ *   scoring (cse_prepare_clean, cse_score*, cse_sweep): sr = 16000 and length <= cse_max_score_length(sr)
+ *     (about 38 s: the clean-side STOI kernel keeps the band envelopes of an utterance in shared memory). */
+int cse_max_score_length(int sr);
 int cse_bins_padded(int n_fft);         /* bin stride of the spectrogram layout */
 int cse_num_frames(int length, int hop); /* 1 + length / hop (librosa center=True) */
 
