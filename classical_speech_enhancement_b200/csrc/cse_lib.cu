@@ -140,8 +140,9 @@ static real alg_eps(int algorithm) { return algorithm == CSE_ALG_MMSE ? R(1e-12)
 // items [item0, item0 + n_items) of the utterance-major (utt, param) product
 static int enhance_items(const void* tables, int algorithm, const void* Y, const void* N, int noise_tv, int length,
                          int n_fft, int hop, const cse_params* params, int n_params, int item0, int n_items,
-                         void* out, void* stream) {
+                         void* out, void* stream, const int* item_list = nullptr) {
     EnhanceArgs a;
+    a.item_list = item_list;
     a.T = (const CseTables*)tables; a.Y = (const real2*)Y; a.N = (const real*)N; a.params = params;
     a.out = (real*)out; a.noise_tv = noise_tv; a.L = length; a.hop = hop;
     a.n_frames = cse_num_frames(length, hop); a.n_params = n_params; a.item0 = item0; a.eps = alg_eps(algorithm);
@@ -164,6 +165,17 @@ extern "C" int cse_enhance(const void* tables, int algorithm, const void* Y, con
     CSE_REQUIRE(algorithm >= 0 && algorithm <= 3, "unknown algorithm %d", algorithm);
     return enhance_items(tables, algorithm, Y, N, noise_tv, length, n_fft, hop, params, n_params, 0,
                          n_utts * n_params, out, stream);
+}
+
+extern "C" int cse_enhance_list(const void* tables, int algorithm, const void* Y, const void* N, int noise_tv, int length,
+                                int n_fft, int hop, const cse_params* params, int n_params, const int* items, int n_items,
+                                void* out, void* stream) {
+    CSE_REQUIRE(tables && Y && N && params && out && items, "NULL argument");
+    CSE_REQUIRE(valid_nfft(n_fft), "n_fft %d not in {256,512,1024,2048}", n_fft);
+    CSE_REQUIRE(hop > 0 && hop <= n_fft / 2 && hop % 2 == 0, "hop %d must be even and <= n_fft/2", hop);
+    CSE_REQUIRE(n_params > 0 && n_items > 0 && length > n_fft / 2, "bad sizes");
+    CSE_REQUIRE(algorithm >= 0 && algorithm <= 3, "unknown algorithm %d", algorithm);
+    return enhance_items(tables, algorithm, Y, N, noise_tv, length, n_fft, hop, params, n_params, 0, n_items, out, stream, items);
 }
 
 #include "cse_lib_noise_score.inl"

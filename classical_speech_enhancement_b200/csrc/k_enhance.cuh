@@ -95,7 +95,8 @@ struct EnhanceArgs {
     const real2* Y;      // [U][nf][nbp]
     const real* N;       // [U][nbp] or [U][nf][nbp]
     const cse_params* params;
-    real* out;           // [(item - item0)][L]
+    real* out;           // [(item - item0)][L]  (or [i][L] for item_list[i])
+    const int* item_list; // optional: explicit items (u * n_params + c) of a sparse launch (winners' re-materialisation)
     int noise_tv, L, hop, n_frames, n_params, item0;
     int hop_shift;       // log2(hop) when hop is a power of two, else -1
     real eps;
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
     real2* w2s = reinterpret_cast<real2*>(pv_s + 16);                   // M window pairs (w[2m], w[2m+1])
     real2* tws = w2s + M;                                              // per-pass twiddles of the half-size FFT (FftTwLayout)
     const int tid = threadIdx.x;
-    const int item = a.item0 + blockIdx.x;
+    const int item = a.item_list ? a.item_list[blockIdx.x] : a.item0 + blockIdx.x;
     const int u = item / a.n_params, c = item - u * a.n_params;
     const int nbp = cse_nbp(NFFT);
     const int nf = a.n_frames, L = a.L;

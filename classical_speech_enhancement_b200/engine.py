@@ -544,6 +544,46 @@ class SweepEngine:
                 out[:, members, :] = host[:, r:r + 1, :]
         return out
 
+    def enhance_list(self, alg_name, points, wanted):
+        """Raw enhanced waveforms of a SPARSE set of candidates: ``wanted`` = [(utterance, grid index)] ->
+        {(utterance, grid index): waveform [L]}.  One ``cse_enhance_list`` launch per noise-PSD group that holds
+        wanted points - the winners of a dataset sweep (<= 3 per utterance and algorithm) cost a fraction of a
+        percent of the sweep that found them."""
+        alg = ALGORITHM_IDS[alg_name] if isinstance(alg_name, str) else int(alg_name)
+        pl = self._plan(alg, points)
+        if "point_loc" not in pl:
+            grp = np.zeros(pl["n_points"], dtype=np.int32)
+            row = np.zeros(pl["n_points"], dtype=np.int32)
+            for gi, g in enumerate(pl["groups"]):
+                grp[g["member_idx"]] = gi
+                row[g["member_idx"]] = g["row_idx"]
+            pl["point_loc"] = (grp, row)
+        grp, row = pl["point_loc"]
+        be, lib_ = self.be, self.lib
+        by_group = {}
+        for u, i in wanted:
+            by_group.setdefault(int(grp[i]), []).append((int(u), int(i)))
+        out = {}
+        for gi, lst in by_group.items():
+            g = pl["groups"][gi]
+            key = g["key"]
+            n_fft, hop = key[0], key[1]
+            Y = self.stft(n_fft, hop)
+            N, tv = self.noise(key)
+            uniq = sorted({(u, int(row[i])) for u, i in lst})                 # identical device candidates once
+            items = np.array([u * g["n_rows"] + r for u, r in uniq], dtype=np.int32)
+            params = be.from_host(g["params_host"])
+            dev_items = be.from_host(items)
+            wav = be.empty((len(items), self.L), self.real)
+            lib_.enhance_list(be.ptr(self.tables), alg, be.ptr(Y), be.ptr(N), int(tv), self.L, n_fft, hop, be.ptr(params),
+                              g["n_rows"], be.ptr(dev_items), len(items), be.ptr(wav), be.stream())
+            self.launches += 1
+            host = be.to_host(wav)
+            slot = {ur: k for k, ur in enumerate(uniq)}
+            for u, i in lst:
+                out[(u, i)] = host[slot[(u, int(row[i]))]]
+        return out
+
     def score_waveforms(self, wav, finalize=True):
         """Scores arbitrary waveforms [U, C, L] against this batch's clean signals."""
         wav = np.ascontiguousarray(wav, dtype=self.real)

@@ -281,28 +281,21 @@ def write_wav_pcm16(path, x, sr):
 
 
 def run_algorithm_on_pair(alg_name, alg_fn, param_ranges, clean, noisy, sr, out_dir, stem, *,
-                          pesq_scorer="auto", engine=None, verbose=True):
+                          pesq_scorer="auto", pesq_workers=None, engine=None, verbose=True):
     """Optimise one algorithm for one pair; save the three winners and return the reference's
     result row (``:278-338``).  ``true_noise`` points get the clean signal routed in, as
     ``algorithm_wrapper`` does (``:282-292``) - here the engine owns it."""
     if "clean_audio" not in inspect.signature(alg_fn).parameters and any(
             m == "true_noise" for m in param_ranges.get("noise_method", [])):
         raise ValueError(f"{alg_name} does not support 'true_noise' (no clean_audio parameter)")
-    opt = optimize_parameters(clean, noisy, sr, alg_fn, param_ranges, pesq_scorer=pesq_scorer, engine=engine,
-                              verbose=verbose)
+    opt = optimize_parameters(clean, noisy, sr, alg_fn, param_ranges, pesq_scorer=pesq_scorer, pesq_workers=pesq_workers,
+                              engine=engine, verbose=verbose)
     if out_dir is not None:
         os.makedirs(out_dir, exist_ok=True)
         for key, tag in (("stoi", "stoi"), ("pesq", "pesq"), ("balance", "balanced")):
             write_wav_pcm16(os.path.join(out_dir, f"{stem}_{alg_name}_optimized_{tag}.wav"), opt[key]["enhanced"], sr)
-    return {
-        "alg": alg_name, "stem": stem, "sr": sr,
-        "stoi_noisy": opt["baseline"]["stoi"], "pesq_noisy": opt["baseline"]["pesq"], "snr_noisy": opt["baseline"]["snr"],
-        "stoi_stoiopt": opt["stoi"]["score"], "pesq_stoiopt": opt["stoi"]["pesq"], "snr_stoiopt": opt["stoi"]["snr"],
-        "stoi_pesqopt": opt["pesq"]["stoi"], "pesq_pesqopt": opt["pesq"]["score"], "snr_pesqopt": opt["pesq"]["snr"],
-        "stoi_balopt": opt["balance"]["stoi"], "pesq_balopt": opt["balance"]["pesq"], "snr_balopt": opt["balance"]["snr"],
-        "best_params_stoi": opt["stoi"].get("params", {}), "best_params_pesq": opt["pesq"].get("params", {}),
-        "best_params_balanced": opt["balance"].get("params", {}),
-    }
+    from .results_io import result_row
+    return result_row(alg_name, stem, sr, opt["baseline"], opt)
 
 
 def algorithms_table():

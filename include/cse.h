@@ -149,6 +149,12 @@ int cse_sweep(const void* tables, int algorithm, const void* Y, const void* N, i
 int cse_enhance_items(const void* tables, int algorithm, const void* Y, const void* N, int noise_tv,
                       int length, int n_fft, int hop, const cse_params* params, int n_params,
                       int item0, int n_items, void* out, void* stream);
+/* Sparse form: `items` [dev, int32] lists the n_items (utterance * n_params + param) candidates to compute, out[i][L]
+ * receives candidate items[i].  Used to re-materialise the winners of a sweep (at most three per utterance and
+ * algorithm, Code/speech_enhancement_comparison.py:188-216 keeps their waveforms) without recomputing the grid. */
+int cse_enhance_list(const void* tables, int algorithm, const void* Y, const void* N, int noise_tv,
+                     int length, int n_fft, int hop, const cse_params* params, int n_params,
+                     const int* items, int n_items, void* out, void* stream);
 int cse_score_items(const void* tables, const void* wav, int item0, int n_items, int per_utt,
                     int length, int sr, const void* clean, const void* cache, int finalize,
                     cse_score_t* scores, void* workspace, size_t workspace_bytes, void* stream);

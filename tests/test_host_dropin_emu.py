@@ -1,5 +1,7 @@
 """Host-side drop-in layer (grid planning, dedupe, selection, reference-named entry points)
 exercised end to end without a GPU: the engine runs on the thread-emulated kernels."""
+import os
+
 import numpy as np
 import pytest
 
@@ -209,3 +211,74 @@ def test_dataset_sweep_with_pesq_pool_equals_oracle_selection():
     # dead parameters: one PESQ evaluation serves both noise_percentile values under min_tracking
     pq = out["pesq"]["wiener"][0].reshape(2, 2, 1, 1, 2, 2)
     assert np.array_equal(pq[..., 0, 1], pq[..., 1, 1])
+
+
+def test_run_dataset_rows_wavs_and_resume(tmp_path):
+    """8f-2: the reference's batch loop (``main``, ``:441-471``) as bucketed device sweeps - rows, winner WAVs and
+    result files equal to per-pair ``run_algorithm_on_pair``; all_results.json is the resume record."""
+    import json
+    from scipy.io import wavfile
+    from classical_speech_enhancement_b200 import results_io
+    from classical_speech_enhancement_b200.dataset import find_pairs, processed_stems, run_dataset
+    from classical_speech_enhancement_b200.spectral_subtractor import spectral_subtraction
+    from classical_speech_enhancement_b200.speech_enhancement_comparison import run_algorithm_on_pair, write_wav_pcm16
+    from classical_speech_enhancement_b200.wiener_filter import wiener_filter
+    shape = {"n_fft": [256], "hop_length": [128], "noise_percentile": [10.0], "noise_method": ["percentile", "min_tracking"]}
+    algorithms = [("spectralSubtractor", spectral_subtraction, dict({"alpha": [1.0, 3.0], "beta": [0.01]}, **shape)),
+                  ("wiener", wiener_filter, dict({"alpha": [0.95], "gain_floor": [0.02, 0.1]}, **shape))]
+    data = tmp_path / "data"
+    data.mkdir()
+    raw = {}
+    for u, L in ((0, 9000), (1, 10000), (2, 9000)):
+        c, n = make_pair(u, L)
+        stem = f"p{u:03d}_001"
+        write_wav_pcm16(str(data / f"{stem}_clean.wav"), c, 16000)
+        write_wav_pcm16(str(data / f"{stem}_noisy.wav"), n, 16000)
+        raw[stem] = None
+    pairs = sorted(find_pairs(str(data)), key=lambda p: p["stem"])
+    assert [p["stem"] for p in pairs] == sorted(raw)
+    out_dirs = {a[0]: str(tmp_path / f"results_{a[0]}") for a in algorithms}
+    rows, summary = run_dataset(pairs, out_dirs, str(tmp_path / "summary"), algorithms=algorithms, pesq_scorer=_fake_pesq,
+                                pesq_workers=0, verbose=False)
+    assert len(rows) == 6 and summary["wiener"]["count"] == 3
+    assert processed_stems(out_dirs.values()) == set(raw)
+    # per-pair reference-shaped path on the same prepared signals
+    from classical_speech_enhancement_b200.dataset import _prepare
+    for p in pairs:
+        c, n = _prepare(p, 16000)
+        for name, fn, ranges in algorithms:
+            ref = run_algorithm_on_pair(name, fn, ranges, c, n, 16000, str(tmp_path / "single"), p["stem"],
+                                        pesq_scorer=_fake_pesq, pesq_workers=0, verbose=False)
+            got = next(r for r in rows if r["stem"] == p["stem"] and r["alg"] == name)
+            assert list(got) == list(ref)                                     # same keys, same order
+            for k in ref:
+                if isinstance(ref[k], float):
+                    assert abs(got[k] - ref[k]) < 1e-6, (p["stem"], name, k)
+                else:
+                    assert got[k] == ref[k], (p["stem"], name, k)
+            for tag in ("stoi", "pesq", "balanced"):
+                a = wavfile.read(str(tmp_path / f"results_{name}" / f"{p['stem']}_{name}_optimized_{tag}.wav"))[1]
+                b = wavfile.read(str(tmp_path / "single" / f"{p['stem']}_{name}_optimized_{tag}.wav"))[1]
+                assert np.abs(a.astype(int) - b.astype(int)).max() <= 1
+    # the files statistics.py consumes
+    saved = json.loads((tmp_path / "summary" / "all_results.json").read_text())
+    assert saved == json.loads(json.dumps(rows))
+    for col in ("alg", "stoi_noisy", "pesq_noisy", "stoi_stoiopt", "pesq_stoiopt", "stoi_pesqopt", "pesq_pesqopt",
+                "stoi_balopt", "pesq_balopt", "snr_balopt", "best_params_stoi", "best_params_pesq", "best_params_balanced"):
+        assert col in saved[0]
+    assert saved[0]["best_params_stoi"]["noise_method"] in ("percentile", "min_tracking")
+    header = (tmp_path / "summary" / "all_results.csv").read_text().splitlines()[0]
+    assert header == "stem,alg,stoi_noisy,pesq_noisy,stoi_stoiopt,pesq_stoiopt,stoi_pesqopt,pesq_pesqopt,stoi_balopt,pesq_balopt,snr_balopt"
+    assert list(summary["wiener"]) == ["count"] + [f"{c}_mean" for c in results_io.REPORTED]
+    # resume: nothing left to do; a new pair is appended, existing rows untouched
+    rows2, _ = run_dataset(pairs, out_dirs, str(tmp_path / "summary"), algorithms=algorithms, pesq_scorer=_fake_pesq,
+                           pesq_workers=0, verbose=False)
+    assert rows2 == saved
+    assert run_dataset(pairs, out_dirs, str(tmp_path / "summary"), algorithms=algorithms, resume=True,
+                       pesq_scorer=_fake_pesq, pesq_workers=0, verbose=False)[0] == saved
+    # without PESQ only the stoi winner exists and the PESQ columns are None
+    with pytest.warns(UserWarning):
+        rows3, _ = run_dataset(pairs[:1], {k: str(tmp_path / "nopesq" / k) for k in out_dirs}, str(tmp_path / "summary_nopesq"),
+                               algorithms=algorithms[1:], pesq_scorer=None and "auto" or "auto", verbose=False)
+    assert rows3[0]["pesq_noisy"] is None and rows3[0]["stoi_pesqopt"] is None and rows3[0]["stoi_stoiopt"] is not None
+    assert sorted(os.listdir(tmp_path / "nopesq" / "wiener")) == [f"{pairs[0]['stem']}_wiener_optimized_stoi.wav"]
