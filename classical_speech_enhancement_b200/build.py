@@ -56,8 +56,10 @@ def build_cuda(fp64=False, force=False, verbose=False):
            "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include")]
     if fp64:
         cmd.append("-DCSE_FP64")
-    cmd += SOURCES + ["-o", target]
+    tmp = target + ".part"                 # built aside and renamed: a reader (or a repository snapshot) never sees half a library
+    cmd += SOURCES + ["-o", tmp]
     out = _run(cmd, log=os.path.join(PKG, "build_fp64.log" if fp64 else "build.log"))
+    os.replace(tmp, target)
     if verbose:
         print(out)
     return target
@@ -76,8 +78,10 @@ def build_emu(fp64=False, force=False):
            "-I", os.path.join(ROOT, "tests", "emu"), "-I", os.path.join(ROOT, "include")]
     if fp64:
         cmd.append("-DCSE_FP64")
-    cmd += SOURCES + ["-o", target]
+    tmp = target + ".part"
+    cmd += SOURCES + ["-o", tmp]
     _run(cmd)
+    os.replace(tmp, target)
     return target
 
 
