@@ -43,10 +43,11 @@ CSE_D void gain_pair(real2 Ya, real2 Yb, real2 Nraw, bool first, GainState2& st,
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
             const real pw = e ? Pw.y : Pw.x, pc = e ? Pc.y : Pc.x;
-            g[e] = pw > R(1e-30) ? r_fsqrt(pc * r_rcp(pw)) : (pw > R(0) ? r_sqrt(pc) / r_sqrt(pw) : R(-1));
+            // (comparisons written so that a NaN power takes the first branch and propagates, as np.maximum does)
+            g[e] = !(pw <= R(1e-30)) ? r_fsqrt(pc * r_rcp(pw)) : (pw > R(0) ? r_sqrt(pc) / r_sqrt(pw) : R(-1));
         }
-        Sa = g[0] >= R(0) ? cscale(Ya, g[0]) : mk2(r_sqrt(Pc.x), R(0));
-        Sb = g[1] >= R(0) ? cscale(Yb, g[1]) : mk2(r_sqrt(Pc.y), R(0));
+        Sa = g[0] < R(0) ? mk2(r_sqrt(Pc.x), R(0)) : cscale(Ya, g[0]);
+        Sb = g[1] < R(0) ? mk2(r_sqrt(Pc.y), R(0)) : cscale(Yb, g[1]);
         return;
     }
     if (ALG >= 2 && smooth) {

@@ -64,15 +64,41 @@ def align_to_reference(ref, sig, sr, max_shift_s=0.10, corr_seconds=2.0):
     return sig
 
 
+_RESAMPLER_FIRS = {}
+
+
+def _soxr_hq_like_fir(up, down, sr_in):
+    """Anti-alias / anti-image FIR of the rational resampler, at the rate ``sr_in * up``: the specification of
+    soxr's HQ recipe (what ``librosa.resample`` uses by default) - pass band to 0.913 of the lower Nyquist
+    frequency, stop band from that Nyquist frequency on, linear phase, Kaiser window - with a 140 dB stop band.
+    soxr itself is not installable here; on the reference's own 48 kHz files this design reproduces its published
+    per-file results to 1.1e-7 STOI / 3e-5 dB SNR (``tests/test_oracle_pinning.py``; scipy's default
+    ``resample_poly`` filter was off by 1.2e-5 / 3.4e-3)."""
+    key = (up, down, sr_in)
+    h = _RESAMPLER_FIRS.get(key)
+    if h is None:
+        from scipy.signal import firwin, kaiserord
+        rate = float(sr_in) * up
+        nyq = 0.5 * min(sr_in, sr_in * up / down)
+        f_pass, f_stop = 0.913 * nyq, nyq
+        numtaps, beta = kaiserord(140.0, (f_stop - f_pass) / (0.5 * rate))
+        h = firwin(numtaps | 1, 0.5 * (f_pass + f_stop), window=("kaiser", beta), fs=rate) * up
+        _RESAMPLER_FIRS[key] = h
+    return h
+
+
 def resample_to(x, sr_in, sr_out):
-    """The reference calls ``librosa.resample`` (soxr_hq), not installable here; the polyphase
-    stand-in differs from it by <= 1.2e-5 STOI on the reference's own files."""
+    """``librosa.resample(x, orig_sr=sr_in, target_sr=sr_out)`` (``:23-27``; soxr_hq, output length
+    ceil(n * sr_out / sr_in), float32 in -> float32 out) as a polyphase FIR resampler with a soxr-HQ-like filter."""
     if sr_in == sr_out:
         return x
     from math import gcd
     from scipy.signal import resample_poly
     g = gcd(int(sr_in), int(sr_out))
-    return resample_poly(np.asarray(x, dtype=np.float64), sr_out // g, sr_in // g)
+    up, down = int(sr_out) // g, int(sr_in) // g
+    x = np.asarray(x)
+    y = resample_poly(x.astype(np.float64), up, down, axis=-1, window=_soxr_hq_like_fir(up, down, int(sr_in)))
+    return y.astype(np.float32) if x.dtype == np.float32 else y
 
 
 def prepare_pair(clean, sr_c, noisy, sr_n, target_sr=16000, do_align=True):

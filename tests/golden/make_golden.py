@@ -2,9 +2,9 @@
 container, where /root/reference exists; the GPU box only sees the outputs).
 
 Outputs (all under tests/golden/):
-* ``p257_090_48k.npz``  - the reference's shipped clean/noisy input pair
-  (``Document/Presentation/lowSTOI_SpectralSubtraction_p257_090/*.wav``, 48 kHz PCM16)
-  stored as int16 arrays.
+* ``p257_090_48k.npz``, ``p257_135_48k.npz`` - the reference's two shipped clean/noisy input pairs
+  (``Document/Presentation/lowSTOI_SpectralSubtraction_p257_090/*.wav``, ``.../wiener_p257_135/*.wav``,
+  48 kHz PCM16) stored as int16 arrays.
 * ``published_rows.json`` - every (stem, algorithm, params) -> (STOI, SNR) row the
   reference published for the two stems whose audio ships
   (``Code/results_summary/{20,21,22,28,29}_*/all_results.json``), with the run id and a
@@ -46,8 +46,9 @@ def main():
 
     pairs = {"p257_090": prepare_48k_pair(clean, noisy)}
     d2 = f"{REF}/Document/Presentation/wiener_p257_135"
-    pairs["p257_135"] = prepare_48k_pair(wavfile.read(f"{d2}/p257_135_clean.wav")[1],
-                                         wavfile.read(f"{d2}/p257_135_noisy.wav")[1])
+    c135, n135 = wavfile.read(f"{d2}/p257_135_clean.wav")[1], wavfile.read(f"{d2}/p257_135_noisy.wav")[1]
+    np.savez_compressed(f"{HERE}/p257_135_48k.npz", clean=c135, noisy=n135, sr=48000)
+    pairs["p257_135"] = prepare_48k_pair(c135, n135)
     rows, seen = [], set()
     for run in (20, 21, 22, 28, 29):
         path = glob.glob(f"{REF}/Code/results_summary/{run}_*/all_results.json")[0]
@@ -64,7 +65,9 @@ def main():
                 fn = oracle.ALGORITHMS[r["alg"]]
                 kw = {"clean_audio": c} if p.get("noise_method") == "true_noise" else {}
                 sc = score_candidate(c, fn(n, 16000, **kw, **p), 16000)
-                ok = abs(sc["stoi"] - r["stoi_" + kk]) < 2e-5 and abs(sc["snr"] - r["snr_" + kk]) < 5e-3
+                # "reproducible" = the committed reference code regenerates the row; decided here with the oracle, and
+                # cross-checked by SURVEY.md 8c's independent scratch restatement (same 22 rows)
+                ok = abs(sc["stoi"] - r["stoi_" + kk]) < 5e-7 and abs(sc["snr"] - r["snr_" + kk]) < 2e-4
                 rows.append({"run": run, "source": os.path.relpath(path, REF), "stem": r["stem"],
                              "alg": r["alg"], "criterion": crit, "params": p,
                              "stoi": r["stoi_" + kk], "snr": r["snr_" + kk], "pesq": r["pesq_" + kk],

@@ -11,8 +11,8 @@ import oracle
 from oracle.search import score_candidate
 from tests.golden_util import load_p257_090, published_rows
 
-STOI_TOL = 2e-5     # residual of the resample_poly-for-soxr_hq substitution (see golden_util)
-SNR_TOL = 5e-3      # dB
+STOI_TOL = 5e-7     # observed 1.1e-7 with the soxr-HQ-like resampler design (see golden_util); 1.2e-5 with scipy's default
+SNR_TOL = 2e-4      # dB (observed 3e-5)
 
 
 @pytest.fixture(scope="module")
@@ -42,7 +42,29 @@ def test_published_row(pair, row):
     assert abs(sc["snr"] - row["snr"]) < SNR_TOL
 
 
+ROWS_135 = published_rows("p257_135")
+
+
+@pytest.mark.parametrize("row", ROWS_135, ids=[f"p257_135-run{r['run']}-{r['alg']}-{r['criterion']}" for r in ROWS_135])
+def test_published_row_second_stem(row):
+    """The reference's other shipped pair (``Document/Presentation/wiener_p257_135``): its reproducible rows.
+
+    ``reproducible`` in ``published_rows.json`` was decided by ``make_golden.py`` with this oracle; what keeps that
+    from being circular is SURVEY.md 8c's independent scratch restatement, which reproduces the same 22 of 38 rows
+    (the other 16 come from older code / grids, see ``test_q_semantics_of_stale_row``), and the fact that a row
+    matching to 5e-7 STOI and 2e-4 dB by accident is not a plausible failure mode."""
+    from tests.golden_util import load_pair
+    c, n = load_pair("p257_135")
+    p = row["params"]
+    kw = {"clean_audio": c} if p["noise_method"] == "true_noise" else {}
+    sc = score_candidate(c, oracle.ALGORITHMS[row["alg"]](n, 16000, **kw, **p), 16000)
+    assert abs(oracle.stoi(c, n, 16000) - row["stoi_noisy"]) < STOI_TOL
+    assert abs(sc["stoi"] - row["stoi"]) < STOI_TOL
+    assert abs(sc["snr"] - row["snr"]) < SNR_TOL
+
+
 def test_rows_cover_all_algorithms_and_methods():
+    assert len(ROWS) == 17 and len(ROWS_135) == 5
     algs = {r["alg"] for r in ROWS}
     methods = {r["params"]["noise_method"] for r in ROWS}
     shapes = {(r["params"]["n_fft"], r["params"]["hop_length"]) for r in ROWS}
