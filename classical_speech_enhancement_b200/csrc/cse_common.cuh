@@ -99,6 +99,26 @@ CSE_D real r_fexp2(real x) { real y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) 
 CSE_D real r_flog2(real x) { real y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 CSE_D real r_fsqrt(real x) { real y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return x * y; }
 #endif
+// Shared-memory accesses through 32-bit shared-window addresses (ld.shared / st.shared with a register
+// address): hot loops that hold a few base addresses in registers and index them with packed byte offsets
+// get LDS / STS with no generic-pointer arithmetic around them.  Under the CPU emulation an "address" is the
+// byte offset from the CTA's dynamic shared memory.
+#if defined(CSE_EMU)
+CSE_D unsigned cse_saddr(const void* p) { return (unsigned)((const unsigned char*)p - cse_emu::dyn_smem()); }
+CSE_D real2 cse_lds_r2(unsigned a) { return *reinterpret_cast<const real2*>(cse_emu::dyn_smem() + a); }
+CSE_D uint2 cse_lds_u2(unsigned a) { return *reinterpret_cast<const uint2*>(cse_emu::dyn_smem() + a); }
+CSE_D void cse_sts_r2(unsigned a, real2 v) { *reinterpret_cast<real2*>(cse_emu::dyn_smem() + a) = v; }
+#else
+CSE_D unsigned cse_saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+CSE_D uint2 cse_lds_u2(unsigned a) { uint2 v; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a)); return v; }
+#ifdef CSE_FP64
+CSE_D real2 cse_lds_r2(unsigned a) { real2 v; asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a)); return v; }
+CSE_D void cse_sts_r2(unsigned a, real2 v) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.x), "d"(v.y) : "memory"); }
+#else
+CSE_D real2 cse_lds_r2(unsigned a) { real2 v; asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a)); return v; }
+CSE_D void cse_sts_r2(unsigned a, real2 v) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory"); }
+#endif
+#endif
 // Two-lane ("packed pair") helpers: the same scalar computation for two independent values held
 // in the halves of a real2.  Arithmetic maps to FADD2 / FMUL2 / FFMA2 on sm_100a; min/max and the
 // MUFU functions have no packed form and are applied per half.

@@ -113,17 +113,43 @@ extern "C" int cse_stft_psd(const void* tables, const void* wav, const void* min
 }
 
 // ------------------------------------------------------------------ K3+K4 gain + ISTFT
+// Dynamic shared memory of enhance_kernel<ALG, LOG2N, STAGED> (must mirror the carve-up at the top of the kernel):
+// FFT buffer + zero cell, overlap-add ring, steady-state window sum-of-squares, parameter slots, window pairs,
+// per-pass twiddles, the gather plan for the positions this hop needs, 1/(N wss) pairs, then (128-byte aligned)
+// the TMA tile of F frames of Y (+ of a time-varying noise PSD) and its mbarrier.
+#ifndef CSE_ENH_STAGED_MAX_LOG2N
+#define CSE_ENH_STAGED_MAX_LOG2N 10
+#endif
+#ifndef CSE_ENH_STAGED_MIN_LOG2N
+#define CSE_ENH_STAGED_MIN_LOG2N 8
+#endif
+template <int LOG2N>
+static size_t enhance_smem_bytes(int hop, int noise_tv, bool staged) {
+    typedef EnhanceCfg<LOG2N> C;
+    const int W = C::NFFT + (C::F - 1) * hop;
+    const int kused = (W / 2 + C::NT - 1) / C::NT;
+    size_t s = (size_t)(C::F * C::XST + 1) * sizeof(real2) + (size_t)(W + hop + 16) * sizeof(real) +
+               (size_t)(C::M + FftTwLayout<LOG2N - 1, true>::SIZE) * sizeof(real2) +
+               (size_t)kused * ((C::F + 1) / 2) * C::NT * sizeof(uint2) + (size_t)(hop / 2) * sizeof(real2);
+    s += 128;                                                        // alignment slack of the tile
+    if (staged) s += (size_t)C::F * cse_nbp(C::NFFT) * (sizeof(real2) + (noise_tv ? sizeof(real) : 0));
+    return s + 16;                                                   // mbarrier
+}
 template <int ALG, int LOG2N>
 static int launch_enhance(const EnhanceArgs& a, int n_items, void* stream) {
     typedef EnhanceCfg<LOG2N> C;
-    const int W = C::NFFT + (C::F - 1) * a.hop;
-    const size_t smem = (size_t)(C::F * C::XST + 1) * sizeof(real2) + (size_t)(W + a.hop + 16) * sizeof(real) + (size_t)(C::M + FftTwLayout<LOG2N - 1, true>::SIZE) * sizeof(real2) +
-                        (size_t)C::KMAX * ((C::F + 1) / 2) * C::NT * 2 * sizeof(unsigned) + (size_t)2 * C::NT * sizeof(real2);
-    auto kfn = enhance_kernel<ALG, LOG2N>;
-    const int hop_max = C::NFFT / 2;                                  // the opt-in covers every hop this instantiation accepts
-    const size_t smem_max = smem + (size_t)((C::F - 1) * (hop_max - a.hop) + (hop_max - a.hop)) * sizeof(real);
-    CSE_SMEM_OPT_IN(kfn, smem_max);
-    CSE_LAUNCH(kfn, n_items, C::NT, smem, stream, a);
+    // n_fft 2048: the tile would cost a resident CTA (see k_enhance.cuh)
+    constexpr bool STAGED = LOG2N <= CSE_ENH_STAGED_MAX_LOG2N && LOG2N >= CSE_ENH_STAGED_MIN_LOG2N;
+    const size_t smem = enhance_smem_bytes<LOG2N>(a.hop, a.noise_tv, STAGED);
+    if (a.noise_tv) {
+        auto kfn = enhance_kernel<ALG, LOG2N, STAGED, true>;
+        CSE_SMEM_OPT_IN(kfn, enhance_smem_bytes<LOG2N>(C::NFFT / 2, 1, STAGED));   // covers every hop of the instantiation
+        CSE_LAUNCH(kfn, n_items, C::NT, smem, stream, a);
+    } else {
+        auto kfn = enhance_kernel<ALG, LOG2N, STAGED, false>;
+        CSE_SMEM_OPT_IN(kfn, enhance_smem_bytes<LOG2N>(C::NFFT / 2, 0, STAGED));
+        CSE_LAUNCH(kfn, n_items, C::NT, smem, stream, a);
+    }
     return check_launch("enhance_kernel");
 }
 template <int ALG>

@@ -26,17 +26,63 @@
 #include "cse_fft.cuh"
 #include "cse_special.cuh"
 
+// ---------------------------------------------------------------- TMA bulk copy + mbarrier (sm_100a)
+// The spectrogram layout is frame-major, so the F frames of one iteration are ONE contiguous block of
+// F * nbp bins: a 1-D bulk copy (cp.async.bulk, the TMA engine; SASS UBLKCP) moves it into shared memory
+// without a tensor map, and completion is signalled on an mbarrier (complete_tx::bytes).  One thread
+// issues the copy; nobody spends issue slots, registers or address arithmetic on the tile.
+#if defined(CSE_EMU)
+// CPU emulation (tests): the issuing thread copies synchronously; the CTA barrier at the end of every
+// iteration orders the copy before the next iteration's reads, so waiting is a no-op.
+typedef unsigned long long cse_mbar_t;
+CSE_D void cse_mbar_init(cse_mbar_t*, int) {}
+CSE_D void cse_mbar_expect_tx(cse_mbar_t*, unsigned) {}
+CSE_D void cse_bulk_g2s(void* dst, const void* src, unsigned bytes, cse_mbar_t*) { memcpy(dst, src, bytes); }
+CSE_D void cse_mbar_wait(cse_mbar_t*, unsigned) {}
+#else
+typedef unsigned long long cse_mbar_t;
+CSE_D unsigned cse_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+CSE_D void cse_mbar_init(cse_mbar_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cse_smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+CSE_D void cse_mbar_expect_tx(cse_mbar_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cse_smem_u32(bar)), "r"(bytes) : "memory");
+}
+CSE_D void cse_bulk_g2s(void* dst, const void* src, unsigned bytes, cse_mbar_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(cse_smem_u32(dst)), "l"(src), "r"(bytes), "r"(cse_smem_u32(bar)) : "memory");
+}
+CSE_D void cse_mbar_wait(cse_mbar_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "CSE_MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra CSE_MBAR_DONE_%=;\n"
+        "bra CSE_MBAR_WAIT_%=;\n"
+        "CSE_MBAR_DONE_%=:\n"
+        "}\n" ::"r"(cse_smem_u32(bar)), "r"(parity) : "memory");
+}
+#endif
+
 // The gain rule for two bins at once (the thread's pair (s, M-s)): lane .x = bin a, lane .y = bin b,
 // every FP add / mul / fma issued as one packed instruction for both bins; the decision-directed
 // state (previous gain, previous a-posteriori SNR, smoothed noise PSD) is packed the same way.
 struct GainState2 { real2 g_prev, gam_prev, nsm; };
 
-template <int ALG>
-CSE_D void gain_pair(real2 Ya, real2 Yb, real2 Nraw, bool first, GainState2& st, const real* __restrict__ pv,
+// TV = false (static noise PSD: the percentile estimator, or any method on < 5 frames): the caller passes the
+// PSD already floored at eps and its reciprocal, both loop-invariant - the per-frame floor and the MUFU
+// reciprocal disappear from the frame march (same values, bit-identical results).
+#ifndef CSE_GAIN_TRIM
+#define CSE_GAIN_TRIM 1      // drop clamps that can only bind through rounding (see the comments at each site)
+#endif
+template <int ALG, bool TV>
+CSE_D void gain_pair(real2 Ya, real2 Yb, real2 Nraw, real2 rNstat, bool first, GainState2& st, const real* __restrict__ pv,
                      real eps, bool smooth, real2& Sa, real2& Sb) {
     // |Y|^2 of the two bins with scalar FMAs: gathering (re, re') and (im, im') pairs for a packed form costs eight moves
     const real2 Pw = mk2(r_fma(Ya.x, Ya.x, Ya.y * Ya.y), r_fma(Yb.x, Yb.x, Yb.y * Yb.y));
-    real2 Nt = p_max(Nraw, p_set(eps));
+    real2 Nt = TV ? p_max(Nraw, p_set(eps)) : Nraw;
     if (ALG == 0) {
         const real2 Pc = p_max(p_fma(p_set(-pv[0]), Nt, Pw), p_mul(p_set(pv[1]), Nt));
         real g[2];
@@ -50,13 +96,15 @@ CSE_D void gain_pair(real2 Ya, real2 Yb, real2 Nraw, bool first, GainState2& st,
         Sb = g[1] < R(0) ? mk2(r_sqrt(Pc.y), R(0)) : cscale(Yb, g[1]);
         return;
     }
-    if (ALG >= 2 && smooth) {
+    if (ALG >= 2 && TV && smooth) {
         const real mu = (ALG == 2) ? pv[4] : pv[3];
         if (!first) Nt = p_fma(p_set(mu), st.nsm, p_mul(p_set(pv[9]), Nt));
         st.nsm = Nt;
-        Nt = p_max(Nt, p_set(eps));
+        // a convex combination of two values >= eps: the reference's second floor (mmse.py:57, advanced_mmse.py:66)
+        // can only bind by one rounding of eps itself
+        if (!CSE_GAIN_TRIM) Nt = p_max(Nt, p_set(eps));
     }
-    const real2 gam = p_max(p_mul(Pw, p_rcp(Nt)), p_set(eps));
+    const real2 gam = p_max(p_mul(Pw, TV ? p_rcp(Nt) : rNstat), p_set(eps));
     const real2 gm1 = p_add(gam, p_set(R(-1)));
     const real2 direct = p_max(gm1, p_set(R(0)));
     const real alpha = pv[0];
@@ -64,7 +112,8 @@ CSE_D void gain_pair(real2 Ya, real2 Yb, real2 Nraw, bool first, GainState2& st,
     real2 G;
     if (ALG == 1) {
         const real2 xi = p_max(first ? direct : rec, p_set(R(1e-10)));
-        G = p_clip(p_mul(xi, p_rcp(p_add(xi, p_set(R(1))))), pv[1], R(1));
+        const real2 wg = p_mul(xi, p_rcp(p_add(xi, p_set(R(1)))));                 // xi / (1 + xi) < 1: the upper clip is idle
+        G = CSE_GAIN_TRIM ? p_max(wg, p_set(pv[1])) : p_clip(wg, pv[1], R(1));
     } else {
         const real2 xi = p_max(first ? gm1 : rec, p_set(pv[1]));
         const real2 r = p_rcp(p_add(xi, p_set(R(1))));
@@ -81,7 +130,9 @@ CSE_D void gain_pair(real2 Ya, real2 Yb, real2 Nraw, bool first, GainState2& st,
             // p = 1 / (1 + (1-q) / (q Lambda + eps)), Lambda = exp(v)/(1+xi); numerator and denominator
             // multiplied by exp(-v) so that one exponential serves both E1 and the presence probability
             const real2 A = p_fma(p_set(eps), enegv, p_mul(p_set(q), r));
-            const real2 p = p_clip(p_mul(A, p_rcp(p_fma(p_set(pv[10]), enegv, A))), R(0), R(1));
+            // A > 0 and the denominator exceeds it: p is in (0, 1] up to one rounding, the reference's clip is idle
+            const real2 pr = p_mul(A, p_rcp(p_fma(p_set(pv[10]), enegv, A)));
+            const real2 p = CSE_GAIN_TRIM ? pr : p_clip(pr, R(0), R(1));
             G = p_clip(p_exp2(p_fma(p, p_add(lg2, p_set(-lg2gf)), p_set(lg2gf))), gf, R(1));
         }
     }
@@ -164,7 +215,14 @@ CSE_D void emit_edge_pair(real2 acc, int p, int i, int L, int nf, int hop, int h
 // (E = X[s] + conj X[M-s], O = (X[s] - conj X[M-s]) W_N^-s) needs exactly those two gained bins,
 // so it is formed in registers and written straight into the FFT buffer - no separate split
 // pass, no exchange through shared memory.
-template <int ALG, int LOG2N>
+//
+// STAGED (the product path for n_fft <= 1024): the F frames of Y (and of a time-varying noise PSD) an
+// iteration needs arrive in shared memory by ONE bulk copy each (TMA engine, mbarrier completion), issued
+// by thread 0 right after the gain phase has consumed the previous tile - the copy flies during the FFT and
+// the overlap-add, no thread holds prefetched spectra in registers across those phases, and the gain phase
+// reads its bins with LDS instead of LDG + 64-bit address arithmetic.  !STAGED is the round-1 register
+// prefetch, kept for n_fft = 2048, whose tile would cost a resident CTA.
+template <int ALG, int LOG2N, bool STAGED, bool TV>
 __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT > 200 ? CSE_ENH_MB_LARGE : CSE_ENH_MB_SMALL)) enhance_kernel(EnhanceArgs a) {
     typedef EnhanceCfg<LOG2N> C;
     constexpr int NFFT = C::NFFT, M = C::M, LOG2M = LOG2N - 1, NTB = C::NTB, PPT = C::PPT, NT = C::NT, F = C::F;
@@ -194,6 +252,20 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
     }
     for (int i = tid; i < W; i += NT) ring[i] = R(0);
     if (tid == 0) xs[F * XST] = mk2(R(0), R(0));
+    // shared-memory tail (after the tables whose size depends on the hop): see enhance_smem_bytes()
+    const int W_ = NFFT + (F - 1) * hop;
+    const int kused = (W_ / 2 + NT - 1) / NT;                 // overlap-add pair-positions per thread for THIS hop (<= KMAX)
+    constexpr int F2_ = (F + 1) / 2;
+    // (a byte offset from the shared-memory base, not pointer <-> integer casts: the compiler must keep seeing a
+    // shared-memory pointer, or the tile reads become generic loads with 64-bit address arithmetic)
+    const unsigned tail_off = ((unsigned)((F * XST + 1) * sizeof(real2) + (W_ + hop + 16) * sizeof(real) +
+                                          (M + FftTwLayout<LOG2M, true>::SIZE) * sizeof(real2) +
+                                          (size_t)kused * F2_ * NT * sizeof(uint2) + (size_t)(hop / 2) * sizeof(real2)) + 15u) & ~15u;
+    unsigned char* tail = smem_raw + tail_off;
+    real2* ytile = reinterpret_cast<real2*>(tail);                                    // [F][nbp]  (STAGED)
+    real* ntile = reinterpret_cast<real*>(ytile + (STAGED ? F * cse_nbp(NFFT) : 0));  // [F][nbp]  (STAGED, time-varying noise)
+    cse_mbar_t* bar = reinterpret_cast<cse_mbar_t*>(ntile + ((STAGED && TV) ? F * cse_nbp(NFFT) : 0));
+    if (STAGED && tid == 0) cse_mbar_init(bar, 1);
     for (int m = tid; m < M; m += NT) w2s[m] = mk2(w[2 * m], w[2 * m + 1]);
     load_pass_twiddles<LOG2M, true>(tws, a.T->tw, tid, NT);
     for (int r = tid; r < hop; r += NT) {
@@ -211,16 +283,17 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
     __syncthreads();
     const real* pv = pv_s;                   // parameters stay in shared memory (broadcast reads) to save registers
     const real mu_raw = (ALG == 2) ? (real)a.params[c].v[4] : (ALG == 3) ? (real)a.params[c].v[3] : R(-1);
-    const bool smooth = (ALG >= 2) && a.noise_tv && (mu_raw >= R(0));
+    const bool smooth = (ALG >= 2) && TV && (mu_raw >= R(0));
 
     const real2* __restrict__ Yu = a.Y + (size_t)u * nf * nbp;
-    const real* __restrict__ Nu = a.N + (size_t)u * (a.noise_tv ? (size_t)nf * nbp : (size_t)nbp);
+    const real* __restrict__ Nu = a.N + (size_t)u * (TV ? (size_t)nf * nbp : (size_t)nbp);
     real* __restrict__ out = a.out + (size_t)blockIdx.x * L;
 
     const bool is_pair = tid < NTB, is_mid = tid == NTB;       // lane 0 of the extra warp: bin M/2
     const int n_slots = is_pair ? PPT : (is_mid ? 1 : 0);
     GainState2 st[PPT];
     real nstat[PPT][2];
+    real2 rstat[PPT];
     real2 twc[PPT];                                           // -i W_N^s of each pair slot
     real2 yv[PPT][2][F];
     real nv[PPT][2][F];
@@ -230,9 +303,11 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
 #pragma unroll
     for (int i = 0; i < PPT; ++i) {
         st[i].g_prev = mk2(R(1), R(1)); st[i].gam_prev = mk2(R(1), R(1)); st[i].nsm = mk2(R(0), R(0));
-        nstat[i][0] = (!a.noise_tv && i < n_slots) ? Nu[bin_a(i)] : R(1);
-        nstat[i][1] = (!a.noise_tv && is_pair) ? Nu[bin_b(i)] : R(1);
-        const real2 tws_i = tw_load(a.T->tw, (is_pair ? tid + i * NTB : 0) * (CSE_TW_N / NFFT));
+        // static PSD: floored once here (the algorithms' np.maximum(noise_psd, eps)), reciprocal taken once
+        nstat[i][0] = (!TV && i < n_slots) ? r_max(Nu[bin_a(i)], a.eps) : R(1);
+        nstat[i][1] = (!TV && is_pair) ? r_max(Nu[bin_b(i)], a.eps) : ((!TV && STAGED && i < n_slots) ? r_max(Nu[M / 2], a.eps) : R(1));
+        rstat[i] = mk2(r_rcp(nstat[i][0]), r_rcp(nstat[i][1]));
+        const real2 tws_i = tw_load(a.T->tw, (is_pair ? tid + i * NTB : (STAGED ? M / 2 : 0)) * (CSE_TW_N / NFFT));
         twc[i] = mk2(tws_i.y, -tws_i.x);                      // -i W_N^s: conj-multiplying by it gives i D W_N^-s in one step
     }
     auto fetch = [&](int t0) {
@@ -243,19 +318,19 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
             for (int i = 0; i < PPT; ++i) {
                 if (i < n_slots) {
                     const real2* __restrict__ pa = Yu + row0 + bin_a(i);
-                    const real* __restrict__ na = Nu + (a.noise_tv ? row0 : 0) + bin_a(i);
+                    const real* __restrict__ na = Nu + (TV ? row0 : 0) + bin_a(i);
 #pragma unroll
                     for (int f = 0; f < F; ++f) {
                         yv[i][0][f] = pa[f * nbp];
-                        nv[i][0][f] = a.noise_tv ? na[f * nbp] : nstat[i][0];
+                        nv[i][0][f] = TV ? na[f * nbp] : nstat[i][0];
                     }
                     if (is_pair) {
                         const real2* __restrict__ pb = Yu + row0 + bin_b(i);
-                        const real* __restrict__ nb_ = Nu + (a.noise_tv ? row0 : 0) + bin_b(i);
+                        const real* __restrict__ nb_ = Nu + (TV ? row0 : 0) + bin_b(i);
 #pragma unroll
                         for (int f = 0; f < F; ++f) {
                             yv[i][1][f] = pb[f * nbp];
-                            nv[i][1][f] = a.noise_tv ? nb_[f * nbp] : nstat[i][1];
+                            nv[i][1][f] = TV ? nb_[f * nbp] : nstat[i][1];
                         }
                     }
                 }
@@ -271,10 +346,10 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
                 const int row = t * nbp;
                 const bool on = i < n_slots && t < nf;
                 yv[i][0][f] = on ? Yu[row + ka] : mk2(R(0), R(0));
-                nv[i][0][f] = on ? (a.noise_tv ? Nu[row + ka] : nstat[i][0]) : R(1);
+                nv[i][0][f] = on ? (TV ? Nu[row + ka] : nstat[i][0]) : R(1);
                 const bool onb = on && is_pair;
                 yv[i][1][f] = onb ? Yu[row + kb] : mk2(R(0), R(0));
-                nv[i][1][f] = onb ? (a.noise_tv ? Nu[row + kb] : nstat[i][1]) : R(1);
+                nv[i][1][f] = onb ? (TV ? Nu[row + kb] : nstat[i][1]) : R(1);
             }
         }
     };
@@ -283,7 +358,18 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
     for (int i = 0; i < PPT; ++i)
 #pragma unroll
         for (int f = 0; f < F; ++f) { yv[i][0][f] = mk2(R(0), R(0)); yv[i][1][f] = mk2(R(0), R(0)); nv[i][0][f] = R(1); nv[i][1][f] = R(1); }
-    fetch(0);
+    // STAGED: thread 0 arms the mbarrier with the tile's byte count and issues the bulk copies of the frames
+    // [t0, min(t0 + F, nf)) - contiguous in the frame-major layout - into the shared-memory tile.
+    auto issue_tile = [&](int t0) {
+        const int rows = nf - t0 < F ? nf - t0 : F;
+        const unsigned yb = (unsigned)(rows * nbp * sizeof(real2)), nbytes = TV ? (unsigned)(rows * nbp * sizeof(real)) : 0u;
+        cse_mbar_expect_tx(bar, yb + nbytes);
+        cse_bulk_g2s(ytile, Yu + (size_t)t0 * nbp, yb, bar);
+        if (TV) cse_bulk_g2s(ntile, Nu + (size_t)t0 * nbp, nbytes, bar);
+    };
+    unsigned tile_parity = 0;
+    if (STAGED) { if (tid == 0) issue_tile(0); }        // (the mbarrier was initialised before the barriers above)
+    else fetch(0);
 
     // Overlap-add gather plan.  Thread owns window pair-positions jj = tid + k*NT; frame f of an
     // iteration contributes its sample pair m = jj - f*hop/2 (if 0 <= m < M), which sits at a fixed
@@ -302,6 +388,7 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
     unsigned gcount = 0;                                                              // warp-uniform entry count per k, 4 bits each
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) {
+        if (k >= kused) break;                   // (uniform) the table only holds the positions this hop needs
         const int jj = tid + k * NT;
         unsigned d[2 * F2];
         int n = 0;
@@ -327,13 +414,23 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
 
     // Steady-state normalisation of the pairs this thread emits (window positions j < F*hop): the
     // window sum-of-squares only depends on j mod hop there, so 1/(N * wss) is loop-invariant.
-    real2* inv_ws_s = reinterpret_cast<real2*>(zoff_s + KMAX * F2 * NT);      // [KEMIT][NT]
+    real2* inv_ws_s = reinterpret_cast<real2*>(zoff_s + kused * F2 * NT);     // [hop / 2]: pairs (r, r + 1), r even
+    for (int r2 = tid; r2 < (hop >> 1); r2 += NT)
+        inv_ws_s[r2] = mk2(R(1) / ((real)NFFT * wsteady[2 * r2]), R(1) / ((real)NFFT * wsteady[2 * r2 + 1]));
+    // Steady-state overlap-add (interior iterations, power-of-two hop): everything below is loop-invariant per
+    // thread - how many window pair-positions it owns, which of them finish (are emitted) in an iteration - and
+    // the loop runs on 32-bit shared-window addresses held in registers.
+    const unsigned ring_a = cse_saddr(ring), xs_a = cse_saddr(xs), w2s_a = cse_saddr(w2s), inv_a = cse_saddr(inv_ws_s);
+    const unsigned zoff_a = cse_saddr(zoff_s) + (unsigned)(tid * sizeof(uint2));
+    int kcnt = 0;
+    unsigned emask = 0;
 #pragma unroll
-    for (int k = 0; k < KEMIT; ++k) {
-        const int j = 2 * (tid + k * NT);
-        const int r0 = j % hop, r1 = (j + 1) % hop;
-        inv_ws_s[k * NT + tid] = (j < F * hop) ? mk2(R(1) / ((real)NFFT * wsteady[r0]), R(1) / ((real)NFFT * wsteady[r1])) : mk2(R(0), R(0));
+    for (int k = 0; k < KMAX; ++k) {
+        if (tid + k * NT < W / 2) ++kcnt;
+        if (2 * (tid + k * NT) < F * hop) emask |= 1u << k;
     }
+    const bool fast_ok = a.hop_shift >= 0 && ((L & 1) == 0);
+    __syncthreads();                         // inv_ws_s is read by other threads than its writers
 
     const int total_pos = L + M;             // padded positions [0, L + M) must be emitted
     int ring_base = 0;                       // ring slot of padded position t0 * hop
@@ -343,6 +440,7 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
     for (int t0 = 0; t0 * hop < total_pos; t0 += F) {
         const bool any = t0 < nf;
         if (any) {
+            if (STAGED) { cse_mbar_wait(bar, tile_parity); tile_parity ^= 1u; }
 #pragma unroll
             for (int i = 0; i < PPT; ++i) {
                 if (i < n_slots) {
@@ -357,7 +455,24 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
                             continue;
                         }
                         real2 xa, xb;
-                        gain_pair<ALG>(yv[i][0][f], yv[i][1][f], mk2(nv[i][0][f], nv[i][1][f]), t == 0, st[i], pv, a.eps, smooth, xa, xb);
+                        if (STAGED) {
+                            // every thread runs the generic pair formula: the mid lane with s = M/2 (both "bins" are its
+                            // own bin, the two stores hit the same cell with the same value), slot 0 with (DC, Nyquist)
+                            // whose imaginary parts an inverse real FFT ignores
+                            const int sa = is_pair ? s : M / 2, ka = sa, kb = M - sa;
+                            const real2 Ya = ytile[f * nbp + ka], Yb = ytile[f * nbp + kb];
+                            const real2 Nn = TV ? mk2(ntile[f * nbp + ka], ntile[f * nbp + kb]) : mk2(nstat[i][0], nstat[i][1]);
+                            gain_pair<ALG, TV>(Ya, Yb, Nn, rstat[i], t == 0, st[i], pv, a.eps, smooth, xa, xb);
+                            if (sa == 0) { xa.y = R(0); xb.y = R(0); }
+                            const real2 cb = mk2(xb.x, -xb.y);                     // conj X[M-s]
+                            const real2 E = cadd(xa, cb), D = csub(xa, cb);
+                            const real2 iO = cmulc(D, twc[i]);                     // i D W_N^-s (twc holds -i W_N^s)
+                            const real2 T = csub(E, iO);
+                            xf[SIDX(sa)] = cadd(E, iO);                            // E + iO
+                            if (sa > 0) xf[SIDX(M - sa)] = mk2(T.x, -T.y);         // conj(E) + i conj(O) = conj(E - iO)
+                            continue;
+                        }
+                        gain_pair<ALG, TV>(yv[i][0][f], yv[i][1][f], mk2(nv[i][0][f], nv[i][1][f]), rstat[i], t == 0, st[i], pv, a.eps, smooth, xa, xb);
                         if (!is_pair) { xf[SIDX(M / 2)] = mk2(R(2) * xa.x, R(-2) * xa.y); continue; }   // 2 conj X[M/2]
                         if (s == 0) { xf[0] = mk2(xa.x + xb.x, xa.x - xb.x); continue; }                // DC, Nyquist (real)
                         const real2 cb = mk2(xb.x, -xb.y);                     // conj X[M-s]
@@ -370,8 +485,11 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
                 }
             }
             __syncthreads();
+            // the tile has been consumed by every thread: refill it for the next iteration while the FFT and
+            // the overlap-add run (reads through the generic proxy are ordered before the copy by the barrier)
+            if (STAGED && tid == 0 && t0 + F < nf) issue_tile(t0 + F);
             fft_dif<LOG2M, true, 0>(xs, F, XST, tws, tid, NT);
-            fetch(t0 + F);                   // next iteration's spectra fly during the overlap-add (issued after
+            if (!STAGED) fetch(t0 + F);      // next iteration's spectra fly during the overlap-add (issued after
                                              // the FFT so that they are not live across its register-hungry passes)
         }
         // overlap-add the F windowed frames two samples at a time (sample pair 2m,2m+1 of a frame
@@ -380,6 +498,33 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
         const int emit_end = p_begin + F * hop;
         // steady state: all frames covering the emitted positions exist and the positions map inside [0, L)
         const bool steady = p_begin >= NFFT && t0 + F <= nf && p_begin >= M && emit_end <= L + M;
+        if (steady && fast_ok) {
+            const unsigned rb = (unsigned)(ring_base * sizeof(real)), Wb = (unsigned)(W * sizeof(real));
+            real* __restrict__ outp = out + (p_begin - M);
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                if (k < kcnt) {
+                    unsigned so = rb + (unsigned)((tid + k * NT) * 2 * sizeof(real));
+                    if (so >= Wb) so -= Wb;
+                    real2 acc = cse_lds_r2(ring_a + so);
+                    const int ng = (gcount >> (4 * k)) & 15;
+#pragma unroll
+                    for (int f2 = 0; f2 < F2; ++f2) {
+                        if (2 * f2 < ng) {
+                            const uint2 d = cse_lds_u2(zoff_a + (unsigned)((k * F2 + f2) * NT * sizeof(uint2)));
+                            acc = cfma2(cse_lds_r2(xs_a + (d.x & 0xffffu)), cse_lds_r2(w2s_a + (d.x >> 16)), acc);
+                            acc = cfma2(cse_lds_r2(xs_a + (d.y & 0xffffu)), cse_lds_r2(w2s_a + (d.y >> 16)), acc);
+                        }
+                    }
+                    const bool emit = (emask >> k) & 1u;
+                    cse_sts_r2(ring_a + so, emit ? mk2(R(0), R(0)) : acc);
+                    if (emit) {
+                        const real2 iw = cse_lds_r2(inv_a + (unsigned)(((tid + k * NT) & (hh - 1)) * sizeof(real2)));
+                        *reinterpret_cast<real2*>(outp + 2 * (tid + k * NT)) = mk2(acc.x * iw.x, acc.y * iw.y);
+                    }
+                }
+            }
+        } else
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
             const int jj = tid + k * NT;
@@ -407,7 +552,7 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
                 const int i = p - M;
                 if (steady && vec2 && k < KEMIT) {
                     // interior of the signal: every covering frame exists, all samples are in range
-                    const real2 iw = inv_ws_s[k * NT + tid];
+                    const real2 iw = inv_ws_s[(j % hop) >> 1];
                     *reinterpret_cast<real2*>(out + i) = mk2(acc.x * iw.x, acc.y * iw.y);
                 } else if (i >= -1 && i < L) {
                     emit_edge_pair<NFFT>(acc, p, i, L, nf, hop, a.hop_shift, scale, vec2, w, wsteady, out);
