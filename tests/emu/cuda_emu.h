@@ -19,6 +19,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <map>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -65,6 +67,8 @@ struct BlockCtx {
     unsigned char* smem;
     unsigned nthreads;
     std::atomic<int> orflag[2];     // __syncthreads_or, alternating by call parity
+    std::mutex named_mu;            // named barriers (bar.sync id, count), created on first use
+    std::map<int, pthread_barrier_t*> named;
 };
 struct Tls { BlockCtx* blk; unsigned lane, warp, orphase; };
 extern thread_local Tls tls;
@@ -89,6 +93,23 @@ static inline int __syncthreads_or(int pred) {
     if (t.lane == 0 && t.warp == 0) f.store(0);     // next use of this flag is two calls (>= two barriers) away
     return r;
 }
+namespace cse_emu {
+// bar.sync id, count: the `count` threads of the block that name barrier `id` meet (always the same threads per id).
+static inline void named_barrier(int id, unsigned count) {
+    BlockCtx* b = tls.blk;
+    pthread_barrier_t* bar;
+    {
+        std::lock_guard<std::mutex> g(b->named_mu);
+        auto it = b->named.find(id);
+        if (it == b->named.end()) {
+            bar = new pthread_barrier_t;
+            pthread_barrier_init(bar, nullptr, count);
+            b->named[id] = bar;
+        } else bar = it->second;
+    }
+    pthread_barrier_wait(bar);
+}
+}  // namespace cse_emu
 static inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&cse_emu::tls.blk->warp_bar[cse_emu::tls.warp]); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence_block() { std::atomic_thread_fence(std::memory_order_seq_cst); }
@@ -198,6 +219,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
         for (BlockCtx* c : ctxs) {
             pthread_barrier_destroy(&c->block_bar);
             for (auto& wb : c->warp_bar) pthread_barrier_destroy(&wb);
+            for (auto& nb : c->named) { pthread_barrier_destroy(nb.second); delete nb.second; }
             free(c->smem);
             delete c;
         }
