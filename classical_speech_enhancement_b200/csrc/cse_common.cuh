@@ -119,6 +119,13 @@ CSE_D real2 cse_lds_r2(unsigned a) { real2 v; asm volatile("ld.shared.v2.f32 {%0
 CSE_D void cse_sts_r2(unsigned a, real2 v) { asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory"); }
 #endif
 #endif
+// Makes a register value opaque to the optimiser (it can then neither be re-derived nor folded): used where the
+// compiler would rather recompute loop-invariant index data inside a hot loop than keep it in a register.
+#if defined(CSE_EMU)
+#define CSE_OPAQUE(x) ((void)0)
+#else
+#define CSE_OPAQUE(x) asm volatile("" : "+r"(x))
+#endif
 // Two-lane ("packed pair") helpers: the same scalar computation for two independent values held
 // in the halves of a real2.  Arithmetic maps to FADD2 / FMUL2 / FFMA2 on sm_100a; min/max and the
 // MUFU functions have no packed form and are applied per half.

@@ -83,10 +83,26 @@ template <int Q, int NGRP> CSE_D int fft_group(int t) {
     return t;
 }
 
+// Barrier among the GROUP consecutive threads that own one transform of a batch (butterfly idx -> transform
+// idx / GROUP stays fixed from pass to pass when every thread has one butterfly per pass): a warp barrier when the
+// group fits a warp, else a named barrier of its own - the other transforms' warps run on.
+template <int GROUP>
+CSE_D void fft_group_sync(int tid) {
+    if (GROUP <= 32) { __syncwarp(); return; }
+#if defined(CSE_EMU)
+    cse_emu::named_barrier(1 + tid / GROUP, GROUP);
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(1 + tid / GROUP), "n"(GROUP) : "memory");
+#endif
+}
+
 // One pass of RL fused DIF stages (CONJ: conjugated twiddles = inverse transform).  `h` = half size of the first fused stage,
 // q = h >> (RL-1) = smallest butterfly distance of the pass.
 // ZHI: the upper half of every transform's input is known to be zero (zero-padded frames) and is not read.
-template <int LOG2N, int RL, bool CONJ, int H, int TWN, bool ZHI = false>
+// NAT (last pass only, q == 1, one butterfly per thread): the outputs go to NATURAL order, unpadded -
+// out[b * bstride + k] = X_b[k] - instead of staying bit-reversed in place; the threads of a transform meet
+// between their loads and these scattered stores (fft_group_sync), so the buffer is reused in place.
+template <int LOG2N, int RL, bool CONJ, int H, int TWN, bool ZHI = false, bool NAT = false>
 CSE_D void dif_pass(real2* s, int nbatch, int bstride, const real2* __restrict__ tw, int tid, int nth) {
     constexpr int N = 1 << LOG2N;
     constexpr int NB = 1 << RL;               // elements per butterfly
@@ -101,7 +117,9 @@ CSE_D void dif_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
     constexpr int coff = 3 * (q - 1) / 7;
     for (int idx = tid; idx < total; idx += nth) {
         const int b = idx / per, r = idx - b * per;
-        const int j = r & (q - 1), grp = fft_group<q, per / q>(r / q);
+        // NAT: thread r takes butterfly group brev(r), so that its outputs X[brev_RL(m) << (LOG2N-RL) | r] are
+        // consecutive across the lanes of a warp (conflict-free natural-order stores; the padded loads stay conflict-free)
+        const int j = r & (q - 1), grp = NAT ? (int)(__brev((unsigned)r) >> (32 - (LOG2N - RL))) : fft_group<q, per / q>(r / q);
         // SIDX(base + m q) == SIDX(base) + SIDX(m q): base = grp*NB*q + j with j < q, q a power of two,
         // so neither the >>4 nor the >>8 term of the padding ever carries across the addition.
         real2* p = s + b * bstride + SIDX(grp * (q * NB) + j);
@@ -124,6 +142,15 @@ CSE_D void dif_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
         } else {
             const real2 w1 = U1 ? mk2(R(1), R(0)) : TWN > 0 ? tw_load(tw, j * twstep) : tw_load(tw, coff + j);
             real2 d = csub(v[0], v[1]); v[0] = cadd(v[0], v[1]); v[1] = twmul<CONJ, U1>(d, w1);
+        }
+        if (NAT) {
+            static_assert(!NAT || q == 1, "natural-order output is for the last pass");
+            fft_group_sync<per>(tid);
+            // position grp*NB + m holds X[brev(grp*NB + m)] = X[brev_RL(m) << (LOG2N - RL) | brev(grp)], brev(grp) = r
+            real2* o = s + b * bstride + r;
+#pragma unroll
+            for (int m = 0; m < NB; ++m) o[(int)(__brev((unsigned)m) >> (32 - RL)) << (LOG2N - RL)] = v[m];
+            continue;
         }
 #pragma unroll
         for (int m = 0; m < NB; ++m) p[SIDX(m * q)] = v[m];
@@ -174,20 +201,32 @@ CSE_D void dit_pass(real2* s, int nbatch, int bstride, const real2* __restrict__
 // Decimation-in-frequency transform, natural-order in -> bit-reversed out.  INV=false: forward
 // (e^-j); INV=true: unnormalised inverse (e^+j).  Ends with a __syncthreads().  Stage sizes are
 // template constants so that all index arithmetic folds to shifts and masks.
-template <int LOG2N, bool INV, int TWN = CSE_TW_N, bool ZHI = false>
+// Barrier between two passes whose butterflies of one transform stay with the same GROUP threads (every
+// radix-8 pass of a transform with LOG2N % 3 == 0 maps butterfly idx to transform idx / (N/8)): only those
+// threads have to meet, on a named barrier of their own - the other transforms' warps run on.
+// GROUPSYNC (every thread has exactly one butterfly per pass: nbatch * N/8 <= nth): the barriers between
+// radix-8 passes only gather the N/8 threads of each transform.  NAT: natural-order, unpadded output (see dif_pass).
+template <int LOG2N, bool INV, int TWN = CSE_TW_N, bool ZHI = false, bool GROUPSYNC = false, bool NAT = false>
 CSE_D void fft_dif(real2* s, int nbatch, int bstride, const real2* __restrict__ tw, int tid, int nth,
                    const real2* __restrict__ twg = nullptr) {
     constexpr int REM = LOG2N % 3, NP = LOG2N / 3;
     constexpr int H0 = 1 << (LOG2N - 1), H1 = H0 >> REM;
     constexpr int TWR = TWN < 0 ? CSE_TW_N : TWN;          // remainder pass: flat global table when TWN == -1
     constexpr int TW3 = TWN < 0 ? 0 : TWN;                 // radix-8 passes: compact when TWN <= 0
+    constexpr int G = (1 << LOG2N) / 8;                    // threads per transform in a radix-8 pass
+    static_assert(!NAT || NP >= 1, "natural-order output needs a final radix-8 pass");
     const real2* twr = TWN < 0 ? twg : tw;
+    const bool mine = tid < nbatch * G;                    // (GROUPSYNC) this thread owns a butterfly
+    auto sync = [&](bool last) {
+        if (GROUPSYNC && !last) { if (mine) fft_group_sync<G>(tid); }
+        else __syncthreads();
+    };
     if constexpr (REM == 1) { dif_pass<LOG2N, 1, INV, H0, TWR, ZHI>(s, nbatch, bstride, twr, tid, nth); __syncthreads(); }
     if constexpr (REM == 2) { dif_pass<LOG2N, 2, INV, H0, TWR, ZHI>(s, nbatch, bstride, twr, tid, nth); __syncthreads(); }
-    if constexpr (NP >= 1) { dif_pass<LOG2N, 3, INV, H1, TW3, (ZHI && REM == 0)>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
-    if constexpr (NP >= 2) { dif_pass<LOG2N, 3, INV, (H1 >> 3), TW3>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
-    if constexpr (NP >= 3) { dif_pass<LOG2N, 3, INV, (H1 >> 6), TW3>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
-    if constexpr (NP >= 4) { dif_pass<LOG2N, 3, INV, (H1 >> 9), TW3>(s, nbatch, bstride, tw, tid, nth); __syncthreads(); }
+    if constexpr (NP >= 1) { dif_pass<LOG2N, 3, INV, H1, TW3, (ZHI && REM == 0), (NAT && NP == 1)>(s, nbatch, bstride, tw, tid, nth); sync(NP == 1); }
+    if constexpr (NP >= 2) { dif_pass<LOG2N, 3, INV, (H1 >> 3), TW3, false, (NAT && NP == 2)>(s, nbatch, bstride, tw, tid, nth); sync(NP == 2); }
+    if constexpr (NP >= 3) { dif_pass<LOG2N, 3, INV, (H1 >> 6), TW3, false, (NAT && NP == 3)>(s, nbatch, bstride, tw, tid, nth); sync(NP == 3); }
+    if constexpr (NP >= 4) { dif_pass<LOG2N, 3, INV, (H1 >> 9), TW3, false, (NAT && NP == 4)>(s, nbatch, bstride, tw, tid, nth); sync(NP == 4); }
 }
 
 // Decimation-in-time transform, bit-reversed in -> natural-order out.  Ends with a __syncthreads().

@@ -115,7 +115,7 @@ extern "C" int cse_stft_psd(const void* tables, const void* wav, const void* min
 // ------------------------------------------------------------------ K3+K4 gain + ISTFT
 // Dynamic shared memory of enhance_kernel<ALG, LOG2N, STAGED> (must mirror the carve-up at the top of the kernel):
 // FFT buffer + zero cell, overlap-add ring, steady-state window sum-of-squares, parameter slots, window pairs,
-// per-pass twiddles, the gather plan for the positions this hop needs, 1/(N wss) pairs, then (128-byte aligned)
+// per-pass twiddles, 1/(N wss) pairs, then (16-byte aligned)
 // the TMA tile of F frames of Y (+ of a time-varying noise PSD) and its mbarrier.
 #ifndef CSE_ENH_STAGED_MAX_LOG2N
 #define CSE_ENH_STAGED_MAX_LOG2N 10
@@ -127,10 +127,8 @@ template <int LOG2N>
 static size_t enhance_smem_bytes(int hop, int noise_tv, bool staged) {
     typedef EnhanceCfg<LOG2N> C;
     const int W = C::NFFT + (C::F - 1) * hop;
-    const int kused = (W / 2 + C::NT - 1) / C::NT;
-    size_t s = (size_t)(C::F * C::XST + 1) * sizeof(real2) + (size_t)(W + hop + 16) * sizeof(real) +
-               (size_t)(C::M + FftTwLayout<LOG2N - 1, true>::SIZE) * sizeof(real2) +
-               (size_t)kused * ((C::F + 1) / 2) * C::NT * sizeof(uint2) + (size_t)(hop / 2) * sizeof(real2);
+    size_t s = (size_t)(C::F * C::XST + 1) * sizeof(real2) + (size_t)(C::M + FftTwLayout<LOG2N - 1, true>::SIZE + C::M / 2) * sizeof(real2) +
+               (size_t)(16 + W + hop) * sizeof(real);
     s += 128;                                                        // alignment slack of the tile
     if (staged) s += (size_t)C::F * cse_nbp(C::NFFT) * (sizeof(real2) + (noise_tv ? sizeof(real) : 0));
     return s + 16;                                                   // mbarrier

@@ -155,7 +155,7 @@ struct EnhanceArgs {
 };
 
 #ifndef CSE_ENH_MB_SMALL
-#define CSE_ENH_MB_SMALL 4    // resident CTAs per SM asked of ptxas for the <= 200-thread variants (n_fft <= 512)
+#define CSE_ENH_MB_SMALL 5    // resident CTAs per SM asked of ptxas for the <= 200-thread variants (n_fft <= 512)
 #endif
 #ifndef CSE_ENH_MB_LARGE
 #define CSE_ENH_MB_LARGE 3    // same for the 288-thread variants (n_fft >= 1024): 72 registers; 2 (104 registers, no spills) measured slower
@@ -228,14 +228,20 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
     constexpr int NFFT = C::NFFT, M = C::M, LOG2M = LOG2N - 1, NTB = C::NTB, PPT = C::PPT, NT = C::NT, F = C::F;
     constexpr int XST = C::XST;
     CSE_DYN_SMEM(smem_raw);
-    real2* xs = reinterpret_cast<real2*>(smem_raw);                    // F * XST
-    real* ring = reinterpret_cast<real*>(xs + F * XST + 1);            // W (xs[F * XST] is a zero cell, see the gather plan)
+    // Shared memory: the arrays whose size is known at compile time come first, so that their addresses are the
+    // base plus an immediate; the hop-dependent ones (ring, window sums, TMA tile) follow.
+    constexpr int TWSZ = FftTwLayout<LOG2M, true>::SIZE;
+    real2* xs = reinterpret_cast<real2*>(smem_raw);                    // F * XST (+ 1 spare)
+    real2* w2s = xs + F * XST + 1;                                     // M window pairs (w[2m], w[2m+1])
+    real2* tws = w2s + M;                                              // per-pass twiddles of the half-size FFT (FftTwLayout)
+    real2* inv_ws_s = tws + TWSZ;                                      // M/2 (hop/2 used): 1/(N wss) of the emitted pairs
+    real* pv_s = reinterpret_cast<real*>(inv_ws_s + M / 2);            // 8 params + derived constants (16 slots)
+    real* ring = pv_s + 16;                                            // W
+    constexpr unsigned OFF_W2S = (unsigned)((F * XST + 1) * sizeof(real2)), OFF_INV = OFF_W2S + (unsigned)((M + TWSZ) * sizeof(real2));
+    constexpr unsigned OFF_RING = OFF_INV + (unsigned)((M / 2) * sizeof(real2) + 16 * sizeof(real));
     const int hop = a.hop;
     const int W = NFFT + (F - 1) * hop;
     real* wsteady = ring + W;                                          // hop: steady-state window sum-of-squares
-    real* pv_s = wsteady + hop;                                        // 8 params + derived constants (16 slots)
-    real2* w2s = reinterpret_cast<real2*>(pv_s + 16);                   // M window pairs (w[2m], w[2m+1])
-    real2* tws = w2s + M;                                              // per-pass twiddles of the half-size FFT (FftTwLayout)
     const int tid = threadIdx.x;
     const int item = a.item_list ? a.item_list[blockIdx.x] : a.item0 + blockIdx.x;
     const int u = item / a.n_params, c = item - u * a.n_params;
@@ -251,16 +257,11 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
         pv_s[tid] = v;
     }
     for (int i = tid; i < W; i += NT) ring[i] = R(0);
-    if (tid == 0) xs[F * XST] = mk2(R(0), R(0));
     // shared-memory tail (after the tables whose size depends on the hop): see enhance_smem_bytes()
     const int W_ = NFFT + (F - 1) * hop;
-    const int kused = (W_ / 2 + NT - 1) / NT;                 // overlap-add pair-positions per thread for THIS hop (<= KMAX)
-    constexpr int F2_ = (F + 1) / 2;
     // (a byte offset from the shared-memory base, not pointer <-> integer casts: the compiler must keep seeing a
     // shared-memory pointer, or the tile reads become generic loads with 64-bit address arithmetic)
-    const unsigned tail_off = ((unsigned)((F * XST + 1) * sizeof(real2) + (W_ + hop + 16) * sizeof(real) +
-                                          (M + FftTwLayout<LOG2M, true>::SIZE) * sizeof(real2) +
-                                          (size_t)kused * F2_ * NT * sizeof(uint2) + (size_t)(hop / 2) * sizeof(real2)) + 15u) & ~15u;
+    const unsigned tail_off = (OFF_RING + (unsigned)((W_ + hop) * sizeof(real)) + 15u) & ~15u;
     unsigned char* tail = smem_raw + tail_off;
     real2* ytile = reinterpret_cast<real2*>(tail);                                    // [F][nbp]  (STAGED)
     real* ntile = reinterpret_cast<real*>(ytile + (STAGED ? F * cse_nbp(NFFT) : 0));  // [F][nbp]  (STAGED, time-varying noise)
@@ -281,7 +282,6 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
         pv_s[10] = R(1) - pv_s[4];                                      // 1 - q (Log-MMSE)
     }
     __syncthreads();
-    const real* pv = pv_s;                   // parameters stay in shared memory (broadcast reads) to save registers
     const real mu_raw = (ALG == 2) ? (real)a.params[c].v[4] : (ALG == 3) ? (real)a.params[c].v[3] : R(-1);
     const bool smooth = (ALG >= 2) && TV && (mu_raw >= R(0));
 
@@ -371,57 +371,36 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
     if (STAGED) { if (tid == 0) issue_tile(0); }        // (the mbarrier was initialised before the barriers above)
     else fetch(0);
 
-    // Overlap-add gather plan.  Thread owns window pair-positions jj = tid + k*NT; frame f of an
-    // iteration contributes its sample pair m = jj - f*hop/2 (if 0 <= m < M), which sits at a fixed
-    // shared-memory offset in the bit-reversed FFT output: all loop-invariant, computed once.  Per
-    // (k, thread) the contributing frames are listed first, as descriptors
-    //     byte offset of the FFT output in xs | byte offset of the window pair in w2s << 16,
-    // padded with "zero cell x w2s[0]" entries; the loop runs to the warp's largest count (for the
-    // usual hops every lane of a warp has the same count), so there is no per-element test.
+    // Overlap-add.  The last inverse-FFT pass leaves every frame in NATURAL order (cse_fft.cuh, NAT), so the
+    // sample pair m of frame f sits at xs[f * XST + m] and its window pair at w2s[m]: a thread that owns the
+    // window pair-positions jj = tid + k*NT adds, for every frame f of the iteration with 0 <= m = jj - f*hop/2 < M,
+    // x_f[m] * w[m] - two shared loads at (per-thread base) + (per-frame uniform offset) and one packed FMA per
+    // term, no index table.  Which (k, f) terms exist is loop-invariant: one bit each in `fmask`.
     constexpr int KMAX = C::KMAX;
-    constexpr int KEMIT = 2;           // pairs tid, tid+NT: all emitted pairs when F*hop/2 <= 2*NT (hop <= n_fft/4 here); wider hops use the general path
     const int hh = hop >> 1;
-    constexpr int F2 = (F + 1) / 2;
-    static_assert((size_t)(F * XST + 1) * sizeof(real2) < 65536 && (size_t)M * sizeof(real2) < 65536, "16-bit byte offsets");
-    uint2* zoff_s = reinterpret_cast<uint2*>(tws + FftTwLayout<LOG2M, true>::SIZE);   // [KMAX * F2][NT]
-    static_assert(KMAX <= 8 && F <= 15, "gather counts are packed four bits per k");
-    unsigned gcount = 0;                                                              // warp-uniform entry count per k, 4 bits each
+    static_assert(KMAX * F <= 32, "term mask");
+    unsigned fmask = 0;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-        if (k >= kused) break;                   // (uniform) the table only holds the positions this hop needs
-        const int jj = tid + k * NT;
-        unsigned d[2 * F2];
-        int n = 0;
-#pragma unroll
-        for (int f = 0; f < 2 * F2; ++f) d[f] = (unsigned)((F * XST) * sizeof(real2));           // zero cell, window pair 0
+    for (int k = 0; k < KMAX; ++k)
 #pragma unroll
         for (int f = 0; f < F; ++f) {
-            const int m = jj - f * hh;
-            if (jj < W / 2 && m >= 0 && m < M) {
-                const unsigned e = (unsigned)((f * XST + SIDX(brev_n(m, LOG2M))) * sizeof(real2)) | ((unsigned)(m * sizeof(real2)) << 16);
-#pragma unroll
-                for (int q = 0; q < F; ++q) if (q == n) d[q] = e;
-                ++n;
-            }
+            const int jj = tid + k * NT, m = jj - f * hh;
+            if (jj < W / 2 && m >= 0 && m < M) fmask |= 1u << (k * F + f);
         }
-#pragma unroll
-        for (int f2 = 0; f2 < F2; ++f2) zoff_s[(k * F2 + f2) * NT + tid] = make_uint2(d[2 * f2], d[2 * f2 + 1]);
-        unsigned nmax = (unsigned)n;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { const unsigned other = __shfl_xor_sync(0xffffffffu, nmax, o); nmax = other > nmax ? other : nmax; }
-        gcount |= nmax << (4 * k);
-    }
 
     // Steady-state normalisation of the pairs this thread emits (window positions j < F*hop): the
     // window sum-of-squares only depends on j mod hop there, so 1/(N * wss) is loop-invariant.
-    real2* inv_ws_s = reinterpret_cast<real2*>(zoff_s + kused * F2 * NT);     // [hop / 2]: pairs (r, r + 1), r even
     for (int r2 = tid; r2 < (hop >> 1); r2 += NT)
         inv_ws_s[r2] = mk2(R(1) / ((real)NFFT * wsteady[2 * r2]), R(1) / ((real)NFFT * wsteady[2 * r2 + 1]));
     // Steady-state overlap-add (interior iterations, power-of-two hop): everything below is loop-invariant per
     // thread - how many window pair-positions it owns, which of them finish (are emitted) in an iteration - and
     // the loop runs on 32-bit shared-window addresses held in registers.
-    const unsigned ring_a = cse_saddr(ring), xs_a = cse_saddr(xs), w2s_a = cse_saddr(w2s), inv_a = cse_saddr(inv_ws_s);
-    const unsigned zoff_a = cse_saddr(zoff_s) + (unsigned)(tid * sizeof(uint2));
+    // Four values carry the whole steady-state loop; they are made opaque to the compiler (empty asm), which at
+    // this register budget otherwise re-derives them - thread index, masks, window base - inside the loop:
+    //   tb    shared-window address of xs[tid]: every x / window / ring operand is tb + immediate (+ uniform)
+    //   pm    term mask (KMAX*F bits) | emit mask (KMAX bits) << 20 | number of owned positions << 26
+    //   raddr address of this thread's ring slot for k = 0, advanced by F*hop samples per iteration
+    //   rend  end of the ring
     int kcnt = 0;
     unsigned emask = 0;
 #pragma unroll
@@ -429,6 +408,11 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
         if (tid + k * NT < W / 2) ++kcnt;
         if (2 * (tid + k * NT) < F * hop) emask |= 1u << k;
     }
+    static_assert(KMAX * F <= 20 && KMAX <= 6, "packed loop masks");
+    unsigned pm = fmask | (emask << 20) | ((unsigned)kcnt << 26);
+    unsigned tb = cse_saddr(smem_raw) + (unsigned)(tid * sizeof(real2));
+    unsigned raddr = tb + OFF_RING, rend = cse_saddr(ring) + (unsigned)(W * sizeof(real));
+    CSE_OPAQUE(pm); CSE_OPAQUE(tb); CSE_OPAQUE(rend);
     const bool fast_ok = a.hop_shift >= 0 && ((L & 1) == 0);
     __syncthreads();                         // inv_ws_s is read by other threads than its writers
 
@@ -441,6 +425,12 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
         const bool any = t0 < nf;
         if (any) {
             if (STAGED) { cse_mbar_wait(bar, tile_parity); tile_parity ^= 1u; }
+            // the candidate's parameters, read once per iteration: left in shared memory they would be re-read for
+            // every frame (the compiler cannot prove that the spectrum stores of the frame loop do not alias them)
+            real pvr[12];
+#pragma unroll
+            for (int q = 0; q < 12; ++q) pvr[q] = pv_s[q];
+            const real* pv = pvr;
 #pragma unroll
             for (int i = 0; i < PPT; ++i) {
                 if (i < n_slots) {
@@ -488,7 +478,8 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
             // the tile has been consumed by every thread: refill it for the next iteration while the FFT and
             // the overlap-add run (reads through the generic proxy are ordered before the copy by the barrier)
             if (STAGED && tid == 0 && t0 + F < nf) issue_tile(t0 + F);
-            fft_dif<LOG2M, true, 0>(xs, F, XST, tws, tid, NT);
+            static_assert(F * (M / 8) <= NT, "one butterfly per thread and pass");
+            fft_dif<LOG2M, true, 0, false, true, true>(xs, F, XST, tws, tid, NT);   // group barriers, natural-order output
             if (!STAGED) fetch(t0 + F);      // next iteration's spectra fly during the overlap-add (issued after
                                              // the FFT so that they are not live across its register-hungry passes)
         }
@@ -499,28 +490,26 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
         // steady state: all frames covering the emitted positions exist and the positions map inside [0, L)
         const bool steady = p_begin >= NFFT && t0 + F <= nf && p_begin >= M && emit_end <= L + M;
         if (steady && fast_ok) {
-            const unsigned rb = (unsigned)(ring_base * sizeof(real)), Wb = (unsigned)(W * sizeof(real));
-            real* __restrict__ outp = out + (p_begin - M);
+            const unsigned Wb = (unsigned)(W * sizeof(real)), hh8 = (unsigned)(hh * sizeof(real2));
+            real* __restrict__ outp = out + (p_begin - M) + 2 * tid;
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) {
-                if (k < kcnt) {
-                    unsigned so = rb + (unsigned)((tid + k * NT) * 2 * sizeof(real));
-                    if (so >= Wb) so -= Wb;
-                    real2 acc = cse_lds_r2(ring_a + so);
-                    const int ng = (gcount >> (4 * k)) & 15;
+                if (k < (int)(pm >> 26)) {
+                    unsigned ra = raddr + (unsigned)(k * NT * 2 * sizeof(real));
+                    if (ra >= rend) ra -= Wb;
+                    real2 acc = cse_lds_r2(ra);
 #pragma unroll
-                    for (int f2 = 0; f2 < F2; ++f2) {
-                        if (2 * f2 < ng) {
-                            const uint2 d = cse_lds_u2(zoff_a + (unsigned)((k * F2 + f2) * NT * sizeof(uint2)));
-                            acc = cfma2(cse_lds_r2(xs_a + (d.x & 0xffffu)), cse_lds_r2(w2s_a + (d.x >> 16)), acc);
-                            acc = cfma2(cse_lds_r2(xs_a + (d.y & 0xffffu)), cse_lds_r2(w2s_a + (d.y >> 16)), acc);
+                    for (int f = 0; f < F; ++f) {
+                        if ((pm >> (k * F + f)) & 1u) {
+                            const unsigned at = tb + (unsigned)((k * NT + f * XST) * sizeof(real2)) - (unsigned)f * hh8;
+                            acc = cfma2(cse_lds_r2(at), cse_lds_r2(at + OFF_W2S - (unsigned)(f * XST * sizeof(real2))), acc);
                         }
                     }
-                    const bool emit = (emask >> k) & 1u;
-                    cse_sts_r2(ring_a + so, emit ? mk2(R(0), R(0)) : acc);
+                    const bool emit = (pm >> (20 + k)) & 1u;
+                    cse_sts_r2(ra, emit ? mk2(R(0), R(0)) : acc);
                     if (emit) {
-                        const real2 iw = cse_lds_r2(inv_a + (unsigned)(((tid + k * NT) & (hh - 1)) * sizeof(real2)));
-                        *reinterpret_cast<real2*>(outp + 2 * (tid + k * NT)) = mk2(acc.x * iw.x, acc.y * iw.y);
+                        const real2 iw = inv_ws_s[(tid + k * NT) & (hh - 1)];
+                        *reinterpret_cast<real2*>(outp + 2 * k * NT) = mk2(acc.x * iw.x, acc.y * iw.y);
                     }
                 }
             }
@@ -534,15 +523,10 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
             if (slot >= W) slot -= W;
             real2 acc = *reinterpret_cast<real2*>(ring + slot);
             if (any) {                       // frames beyond n_frames were written as zero spectra
-                const int ng = (gcount >> (4 * k)) & 15;
-                const char* xsb = reinterpret_cast<const char*>(xs);
-                const char* wsb = reinterpret_cast<const char*>(w2s);
 #pragma unroll
-                for (int f2 = 0; f2 < F2; ++f2) {
-                    if (2 * f2 >= ng) break;
-                    const uint2 d = zoff_s[(k * F2 + f2) * NT + tid];   // own slots: no synchronisation needed
-                    acc = cfma2(*reinterpret_cast<const real2*>(xsb + (d.x & 0xffffu)), *reinterpret_cast<const real2*>(wsb + (d.x >> 16)), acc);
-                    acc = cfma2(*reinterpret_cast<const real2*>(xsb + (d.y & 0xffffu)), *reinterpret_cast<const real2*>(wsb + (d.y >> 16)), acc);
+                for (int f = 0; f < F; ++f) {
+                    const int m = jj - f * hh;
+                    if (m >= 0 && m < M) acc = cfma2(xs[f * XST + m], w2s[m], acc);
                 }
             }
             // the ring slot is settled first (same address register as the load above), then finished pairs go out
@@ -550,7 +534,7 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
             *reinterpret_cast<real2*>(ring + slot) = emit ? mk2(R(0), R(0)) : acc;
             if (emit) {
                 const int i = p - M;
-                if (steady && vec2 && k < KEMIT) {
+                if (steady && vec2) {
                     // interior of the signal: every covering frame exists, all samples are in range
                     const real2 iw = inv_ws_s[(j % hop) >> 1];
                     *reinterpret_cast<real2*>(out + i) = mk2(acc.x * iw.x, acc.y * iw.y);
@@ -561,6 +545,8 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
         }
         ring_base += F * hop;
         while (ring_base >= W) ring_base -= W;
+        raddr += (unsigned)(F * hop * sizeof(real));
+        while (raddr >= rend) raddr -= (unsigned)(W * sizeof(real));
         __syncthreads();
     }
 }
