@@ -242,3 +242,60 @@ def test_short_signal_branches(L, n_fft, hop):
             ref = oracle.ALGORITHMS[alg](n, 16000, **kw, **p)
             wav = eng.enhance(alg, [p])[0, 0]
             assert np.abs(wav - ref).max() / np.abs(ref).max() < 1e-4, (alg, method, L)
+
+
+def test_run_dataset_on_device_files_and_resume(tmp_path):
+    """8f-2 on the device: the reference's batch loop as bucketed sweeps - winners re-materialised by
+    ``cse_enhance_list``, PCM16 WAVs, ``all_results.json/.csv`` + ``summary_means.json`` with every key
+    ``Code/evaluation/statistics.py`` loads, rows equal to the per-pair ``run_algorithm_on_pair``, resume."""
+    import json
+    from scipy.io import wavfile
+    from classical_speech_enhancement_b200.dataset import _prepare, find_pairs, run_dataset
+    from classical_speech_enhancement_b200.speech_enhancement_comparison import (algorithms_table, run_algorithm_on_pair,
+                                                                                 write_wav_pcm16)
+    shape = {"n_fft": [512, 1024], "hop_length": [128], "noise_percentile": [10.0], "noise_method": ["percentile", "min_tracking"]}
+    small = {"spectralSubtractor": dict({"alpha": [1.0, 3.0], "beta": [0.01, 0.1]}, **shape),
+             "mmse": dict({"alpha": [0.98], "ksi_min": [0.001, 0.1], "gain_min": [0.05], "gain_max": [1.0]}, **shape),
+             "wiener": dict({"alpha": [0.9, 0.98], "gain_floor": [0.02]}, **shape),
+             "omlsa": dict({"alpha": [0.9], "ksi_min": [0.01], "gain_floor": [0.1], "noise_mu": [0.92, 0.98], "q": [0.3, 0.5]}, **shape)}
+    algorithms = [(name, fn, small[name]) for name, fn, _ in algorithms_table()]
+    data = tmp_path / "data"
+    data.mkdir()
+    for u, L in ((0, 24000), (1, 30000), (2, 24000), (3, 24000)):
+        c, n = make_pair(200 + u, L)
+        write_wav_pcm16(str(data / f"p{u:03d}_001_clean.wav"), c, 16000)
+        write_wav_pcm16(str(data / f"p{u:03d}_001_noisy.wav"), n, 16000)
+    pairs = sorted(find_pairs(str(data)), key=lambda p: p["stem"])
+    out_dirs = {a[0]: str(tmp_path / f"results_{a[0]}") for a in algorithms}
+    rows, summary = run_dataset(pairs[:3], out_dirs, str(tmp_path / "summary"), algorithms=algorithms, pesq_scorer=_corr_pesq,
+                                pesq_workers=4, verbose=False)
+    assert len(rows) == 12 and all(summary[a[0]]["count"] == 3 for a in algorithms)
+    p = pairs[1]
+    c, n = _prepare(p, 16000)
+    for name, fn, ranges in algorithms:
+        ref = run_algorithm_on_pair(name, fn, ranges, c, n, 16000, str(tmp_path / "single"), p["stem"], pesq_scorer=_corr_pesq,
+                                    pesq_workers=0, verbose=False)
+        got = next(r for r in rows if r["stem"] == p["stem"] and r["alg"] == name)
+        assert list(got) == list(ref)
+        for k in ref:
+            if isinstance(ref[k], float):
+                assert abs(got[k] - ref[k]) < 1e-6, (name, k)
+            else:
+                assert got[k] == ref[k], (name, k)
+        for tag in ("stoi", "pesq", "balanced"):
+            a = wavfile.read(str(tmp_path / f"results_{name}" / f"{p['stem']}_{name}_optimized_{tag}.wav"))[1]
+            b = wavfile.read(str(tmp_path / "single" / f"{p['stem']}_{name}_optimized_{tag}.wav"))[1]
+            assert a.shape == (30000,) and np.abs(a.astype(int) - b.astype(int)).max() <= 1
+    saved = json.loads((tmp_path / "summary" / "all_results.json").read_text())
+    # the columns Code/evaluation/statistics.py reads (:284-290, :379-388, :495) and the summary / CSV schema
+    for col in ("alg", "stem", "stoi_noisy", "pesq_noisy", "stoi_stoiopt", "pesq_stoiopt", "stoi_pesqopt", "pesq_pesqopt",
+                "stoi_balopt", "pesq_balopt", "snr_balopt", "best_params_stoi", "best_params_pesq", "best_params_balanced"):
+        assert all(col in r for r in saved)
+    assert all(isinstance(r["best_params_balanced"], dict) and "noise_method" in r["best_params_balanced"] for r in saved)
+    assert (tmp_path / "summary" / "all_results.csv").read_text().splitlines()[0] == \
+        "stem,alg,stoi_noisy,pesq_noisy,stoi_stoiopt,pesq_stoiopt,stoi_pesqopt,pesq_pesqopt,stoi_balopt,pesq_balopt,snr_balopt"
+    assert set(json.loads((tmp_path / "summary" / "summary_means.json").read_text())) == {a[0] for a in algorithms}
+    # resume: the fourth pair is appended, the first twelve rows are untouched
+    rows2, summary2 = run_dataset(pairs, out_dirs, str(tmp_path / "summary"), algorithms=algorithms, pesq_scorer=_corr_pesq,
+                                  pesq_workers=4, verbose=False)
+    assert rows2[:12] == saved and len(rows2) == 16 and summary2["omlsa"]["count"] == 4
