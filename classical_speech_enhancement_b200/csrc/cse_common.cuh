@@ -123,8 +123,10 @@ CSE_D void cse_sts_r2(unsigned a, real2 v) { asm volatile("st.shared.v2.f32 [%0]
 // compiler would rather recompute loop-invariant index data inside a hot loop than keep it in a register.
 #if defined(CSE_EMU)
 #define CSE_OPAQUE(x) ((void)0)
+#define CSE_OPAQUE_PTR(x) ((void)0)
 #else
 #define CSE_OPAQUE(x) asm volatile("" : "+r"(x))
+#define CSE_OPAQUE_PTR(x) asm volatile("" : "+l"(x))
 #endif
 // Two-lane ("packed pair") helpers: the same scalar computation for two independent values held
 // in the halves of a real2.  Arithmetic maps to FADD2 / FMUL2 / FFMA2 on sm_100a; min/max and the

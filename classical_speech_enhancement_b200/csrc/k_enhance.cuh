@@ -418,6 +418,12 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
 
     const int total_pos = L + M;             // padded positions [0, L + M) must be emitted
     int ring_base = 0;                       // ring slot of padded position t0 * hop
+    // iterations [t_lo, t_hi) are steady: every frame covering the emitted positions exists (t0*hop >= n_fft,
+    // t0 + F <= n_frames) and the positions map inside [0, L) ((t0 + F)*hop <= L + M)
+    int t_lo = (NFFT + hop - 1) / hop, t_hi = (nf - F < (L + M) / hop - F ? nf - F : (L + M) / hop - F) + 1;
+    if (!fast_ok) t_hi = t_lo;
+    real* outp = out - M + 2 * tid;          // + t0 * hop: where this thread's k = 0 pair of the iteration goes
+    CSE_OPAQUE(t_lo); CSE_OPAQUE(t_hi);
     const real scale = R(1) / (real)NFFT;    // irfft normalisation (1/2 of the split, 1/M of the FFT)
     const bool vec2 = (L & 1) == 0;          // waveform rows 8-byte aligned -> paired stores
 
@@ -488,10 +494,8 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
         const int p_begin = t0 * hop;
         const int emit_end = p_begin + F * hop;
         // steady state: all frames covering the emitted positions exist and the positions map inside [0, L)
-        const bool steady = p_begin >= NFFT && t0 + F <= nf && p_begin >= M && emit_end <= L + M;
-        if (steady && fast_ok) {
+        if (t0 >= t_lo && t0 < t_hi) {
             const unsigned Wb = (unsigned)(W * sizeof(real)), hh8 = (unsigned)(hh * sizeof(real2));
-            real* __restrict__ outp = out + (p_begin - M) + 2 * tid;
 #pragma unroll
             for (int k = 0; k < KMAX; ++k) {
                 if (k < (int)(pm >> 26)) {
@@ -513,7 +517,8 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
                     }
                 }
             }
-        } else
+        } else {
+        const bool steady = p_begin >= NFFT && t0 + F <= nf && p_begin >= M && emit_end <= L + M;
 #pragma unroll
         for (int k = 0; k < KMAX; ++k) {
             const int jj = tid + k * NT;
@@ -543,6 +548,9 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
                 }
             }
         }
+        }
+        outp += F * hop;
+        CSE_OPAQUE_PTR(outp);
         ring_base += F * hop;
         while (ring_base >= W) ring_base -= W;
         raddr += (unsigned)(F * hop * sizeof(real));
