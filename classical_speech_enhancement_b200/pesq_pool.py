@@ -19,10 +19,11 @@ from .engine import finalize_host
 _worker_state = {}
 
 
-def _score_job(job):
-    """Runs in a pool process (or inline): -> [(u, grid indices, value | None)]."""
+def _score_job(job, scorer=None, sr=None):
+    """Runs in a pool process (scorer inherited through the fork) or inline (scorer passed): -> [(u, grid indices, value | None)]."""
     u, idx_lists, clean, wavs, lags, flags = job
-    scorer, sr = _worker_state["scorer"], _worker_state["sr"]
+    if scorer is None:
+        scorer, sr = _worker_state["scorer"], _worker_state["sr"]
     clean = np.asarray(clean, dtype=np.float64)
     out = []
     for j, idx in enumerate(idx_lists):
@@ -50,12 +51,13 @@ class PesqPool:
         if workers is None:
             workers = max(1, min((os.cpu_count() or 2) - 1, 32))
         self.workers = int(workers)
+        self.scorer, self.sr = scorer, sr
         self.results = {}
         self.pending = []
         self.pool = None
-        _worker_state.update(scorer=scorer, sr=sr)
         if self.workers > 0:
             import multiprocessing as mp
+            _worker_state.update(scorer=scorer, sr=sr)      # the children take their copy at the fork below
             self.pool = mp.get_context("fork").Pool(self.workers)
 
     def __enter__(self):
@@ -72,7 +74,7 @@ class PesqPool:
                [np.asarray(w) for w in wavs], None if lags is None else np.asarray(lags),
                None if flags is None else np.asarray(flags))
         if self.pool is None:
-            self._store(_score_job(job))
+            self._store(_score_job(job, self.scorer, self.sr))
         else:
             self.pending.append(self.pool.apply_async(_score_job, (job,)))
 

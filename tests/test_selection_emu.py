@@ -70,3 +70,19 @@ def test_selection_is_order_dependent_not_argmax():
     table["stoi"][0, 35] = np.float32(0.5) + np.float32(2e-6)
     lib.select_best(ptr(table), None, 1, 40, ptr(win), None)
     assert win[0, 0]["index"] == 35
+
+
+def test_pesq_pool_inline_and_forked_scorers_do_not_mix():
+    """Two pools alive at once keep their own scorer (inline: on the instance; forked: the children's copy)."""
+    from classical_speech_enhancement_b200.pesq_pool import PesqPool
+    clean = np.linspace(-0.5, 0.5, 400)
+    wavs = [clean * 0.5, clean * 2.5]            # the second one clips in finalize
+    a = PesqPool(lambda c, w, sr: 1.0 + float(np.abs(w).max()), 16000, workers=0)
+    b = PesqPool(lambda c, w, sr: None if np.abs(w).max() >= 1.0 else 3.0, 16000, workers=2)
+    for pool in (a, b):
+        pool.submit(0, [0, [1, 2]], clean, wavs, lags=np.array([0, 0]), flags=np.array([1, 1]))
+        pool.submit(1, [0], clean, [clean], lags=np.array([3]), flags=np.array([0]))       # invalid candidate: not scored
+    ta, tb = a.table(2, 3), b.table(2, 3)
+    a.close(); b.close()
+    assert np.allclose(ta[0], [1.25, 2.0, 2.0]) and np.isnan(ta[1]).all()
+    assert tb[0, 0] == 3.0 and np.isnan(tb[0, 1]) and np.isnan(tb[0, 2]) and np.isnan(tb[1]).all()
