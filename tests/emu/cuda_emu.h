@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -68,7 +69,7 @@ struct BlockCtx {
     unsigned nthreads;
     std::atomic<int> orflag[2];     // __syncthreads_or, alternating by call parity
     std::mutex named_mu;            // named barriers (bar.sync id, count), created on first use
-    std::map<int, pthread_barrier_t*> named;
+    std::map<int, struct NamedBarrier*> named;
 };
 struct Tls { BlockCtx* blk; unsigned lane, warp, orphase; };
 extern thread_local Tls tls;
@@ -94,21 +95,36 @@ static inline int __syncthreads_or(int pred) {
     return r;
 }
 namespace cse_emu {
-// bar.sync id, count: the `count` threads of the block that name barrier `id` meet (always the same threads per id).
-static inline void named_barrier(int id, unsigned count) {
+// Named barriers (bar.sync id, count / bar.arrive id, count): `count` arrivals complete a phase; bar.sync arrives and
+// waits for the phase to complete, bar.arrive only arrives.  A thread that runs ahead into the next phase of the same
+// barrier waits until the previous phase has completed (the hardware's behaviour for a barrier still in use).
+struct NamedBarrier {
+    std::mutex mu;
+    std::condition_variable cv;
+    unsigned arrived = 0;
+    unsigned long generation = 0;
+};
+static inline NamedBarrier* named_barrier_get(int id) {
     BlockCtx* b = tls.blk;
-    pthread_barrier_t* bar;
-    {
-        std::lock_guard<std::mutex> g(b->named_mu);
-        auto it = b->named.find(id);
-        if (it == b->named.end()) {
-            bar = new pthread_barrier_t;
-            pthread_barrier_init(bar, nullptr, count);
-            b->named[id] = bar;
-        } else bar = it->second;
-    }
-    pthread_barrier_wait(bar);
+    std::lock_guard<std::mutex> g(b->named_mu);
+    auto it = b->named.find(id);
+    if (it == b->named.end()) it = b->named.emplace(id, new NamedBarrier).first;
+    return it->second;
 }
+static inline void named_barrier_op(int id, unsigned count, bool wait) {
+    NamedBarrier* nb = named_barrier_get(id);
+    std::unique_lock<std::mutex> lk(nb->mu);
+    const unsigned long gen = nb->generation;
+    if (++nb->arrived == count) {
+        nb->arrived = 0;
+        ++nb->generation;
+        nb->cv.notify_all();
+    } else if (wait) {
+        nb->cv.wait(lk, [&] { return nb->generation != gen; });
+    }
+}
+static inline void named_barrier(int id, unsigned count) { named_barrier_op(id, count, true); }
+static inline void named_barrier_arrive(int id, unsigned count) { named_barrier_op(id, count, false); }
 }  // namespace cse_emu
 static inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&cse_emu::tls.blk->warp_bar[cse_emu::tls.warp]); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
@@ -219,7 +235,7 @@ void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& bod
         for (BlockCtx* c : ctxs) {
             pthread_barrier_destroy(&c->block_bar);
             for (auto& wb : c->warp_bar) pthread_barrier_destroy(&wb);
-            for (auto& nb : c->named) { pthread_barrier_destroy(nb.second); delete nb.second; }
+            for (auto& nb : c->named) delete nb.second;
             free(c->smem);
             delete c;
         }
