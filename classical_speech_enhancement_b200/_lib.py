@@ -35,6 +35,7 @@ SIGNATURES = {
     "cse_noise_workspace_bytes": (_sz, [_i, _i, _i]),
     "cse_noise_percentile": (_i, [_vp, _i, _i, _i, _d, _d, _vp, _vp, _sz, _vp]),
     "cse_noise_mintrack": (_i, [_vp, _i, _i, _i, _d, _vp, _vp, _sz, _vp]),
+    "cse_gamma": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _d, _d, _vp, _vp]),
     "cse_enhance": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
     "cse_clean_cache_bytes": (_sz, [_i, _i]),
     "cse_clean_workspace_bytes": (_sz, [_i, _i, _i]),

@@ -139,7 +139,14 @@ static int launch_enhance(const EnhanceArgs& a, int n_items, void* stream) {
     // n_fft 2048: the tile would cost a resident CTA (see k_enhance.cuh)
     constexpr bool STAGED = LOG2N <= CSE_ENH_STAGED_MAX_LOG2N && LOG2N >= CSE_ENH_STAGED_MIN_LOG2N;
     const size_t smem = enhance_smem_bytes<LOG2N>(a.hop, a.noise_tv, STAGED);
-    if (a.noise_tv) {
+    if (a.noise_tv == 2) {
+        if constexpr (ALG == 0) return fail(CSE_EINVAL, "spectral subtraction takes the noise PSD, not the a-posteriori SNR (noise_tv 2)");
+        else {
+            auto kfn = enhance_kernel<ALG, LOG2N, STAGED, true, true>;
+            CSE_SMEM_OPT_IN(kfn, enhance_smem_bytes<LOG2N>(C::NFFT / 2, 1, STAGED));
+            CSE_LAUNCH(kfn, n_items, C::NT, smem, stream, a);
+        }
+    } else if (a.noise_tv) {
         auto kfn = enhance_kernel<ALG, LOG2N, STAGED, true>;
         CSE_SMEM_OPT_IN(kfn, enhance_smem_bytes<LOG2N>(C::NFFT / 2, 1, STAGED));   // covers every hop of the instantiation
         CSE_LAUNCH(kfn, n_items, C::NT, smem, stream, a);
@@ -189,6 +196,19 @@ extern "C" int cse_enhance(const void* tables, int algorithm, const void* Y, con
     CSE_REQUIRE(algorithm >= 0 && algorithm <= 3, "unknown algorithm %d", algorithm);
     return enhance_items(tables, algorithm, Y, N, noise_tv, length, n_fft, hop, params, n_params, 0,
                          n_utts * n_params, out, stream);
+}
+
+extern "C" int cse_gamma(const void* Y, const void* N, int noise_tv, int n_utts, int length, int n_fft, int hop,
+                         double noise_mu, double eps, void* G, void* stream) {
+    CSE_REQUIRE(Y && N && G, "NULL argument");
+    CSE_REQUIRE(valid_nfft(n_fft) && hop > 0 && n_utts > 0 && length > n_fft / 2, "bad sizes");
+    CSE_REQUIRE(noise_tv == 0 || noise_tv == 1, "noise_tv must be 0 (static PSD) or 1 (time-varying PSD)");
+    const int nf = cse_num_frames(length, hop), nb = n_fft / 2 + 1, nbp = cse_nbp(n_fft);
+    real mu = (real)noise_mu;
+    if (noise_mu >= 0.0) mu = r_clip(mu, R(0), R(0.9999));               // mmse.py:51, advanced_mmse.py:61
+    CSE_LAUNCH(gamma_kernel, dim3((nbp + 127) / 128, n_utts), 128, 0, stream, (const real2*)Y, (const real*)N, noise_tv, nf, nb,
+               nbp, mu, (real)eps, (real*)G);
+    return check_launch("gamma_kernel");
 }
 
 extern "C" int cse_enhance_list(const void* tables, int algorithm, const void* Y, const void* N, int noise_tv, int length,

@@ -77,11 +77,15 @@ struct GainState2 { real2 g_prev, gam_prev, nsm; };
 #ifndef CSE_GAIN_TRIM
 #define CSE_GAIN_TRIM 1      // drop clamps that can only bind through rounding (see the comments at each site)
 #endif
-template <int ALG, bool TV>
+// GAM = true: `Nraw` IS the a-posteriori SNR gamma = max(|Y|^2 / N', eps), N' the floored (and, for the recursive
+// algorithms, smoothed) noise PSD: everything in front of the decision-directed recursion is the same for all
+// candidates of one (utterance, noise PSD, noise_mu) and is computed once per utterance by gamma_kernel.
+template <int ALG, bool TV, bool GAM = false>
 CSE_D void gain_pair(real2 Ya, real2 Yb, real2 Nraw, real2 rNstat, bool first, GainState2& st, const real* __restrict__ pv,
                      real eps, bool smooth, real2& Sa, real2& Sb) {
+    static_assert(!(GAM && ALG == 0), "spectral subtraction needs the PSD itself");
     // |Y|^2 of the two bins with scalar FMAs: gathering (re, re') and (im, im') pairs for a packed form costs eight moves
-    const real2 Pw = mk2(r_fma(Ya.x, Ya.x, Ya.y * Ya.y), r_fma(Yb.x, Yb.x, Yb.y * Yb.y));
+    const real2 Pw = GAM ? mk2(R(0), R(0)) : mk2(r_fma(Ya.x, Ya.x, Ya.y * Ya.y), r_fma(Yb.x, Yb.x, Yb.y * Yb.y));
     real2 Nt = TV ? p_max(Nraw, p_set(eps)) : Nraw;
     if (ALG == 0) {
         const real2 Pc = p_max(p_fma(p_set(-pv[0]), Nt, Pw), p_mul(p_set(pv[1]), Nt));
@@ -96,7 +100,7 @@ CSE_D void gain_pair(real2 Ya, real2 Yb, real2 Nraw, real2 rNstat, bool first, G
         Sb = g[1] < R(0) ? mk2(r_sqrt(Pc.y), R(0)) : cscale(Yb, g[1]);
         return;
     }
-    if (ALG >= 2 && TV && smooth) {
+    if (ALG >= 2 && TV && !GAM && smooth) {
         const real mu = (ALG == 2) ? pv[4] : pv[3];
         if (!first) Nt = p_fma(p_set(mu), st.nsm, p_mul(p_set(pv[9]), Nt));
         st.nsm = Nt;
@@ -104,7 +108,7 @@ CSE_D void gain_pair(real2 Ya, real2 Yb, real2 Nraw, real2 rNstat, bool first, G
         // can only bind by one rounding of eps itself
         if (!CSE_GAIN_TRIM) Nt = p_max(Nt, p_set(eps));
     }
-    const real2 gam = p_max(p_mul(Pw, TV ? p_rcp(Nt) : rNstat), p_set(eps));
+    const real2 gam = GAM ? Nraw : p_max(p_mul(Pw, TV ? p_rcp(Nt) : rNstat), p_set(eps));
     const real2 gm1 = p_add(gam, p_set(R(-1)));
     const real2 direct = p_max(gm1, p_set(R(0)));
     const real alpha = pv[0];
@@ -222,7 +226,7 @@ CSE_D void emit_edge_pair(real2 acc, int p, int i, int L, int nf, int hop, int h
 // the overlap-add, no thread holds prefetched spectra in registers across those phases, and the gain phase
 // reads its bins with LDS instead of LDG + 64-bit address arithmetic.  !STAGED is the round-1 register
 // prefetch, kept for n_fft = 2048, whose tile would cost a resident CTA.
-template <int ALG, int LOG2N, bool STAGED, bool TV>
+template <int ALG, int LOG2N, bool STAGED, bool TV, bool GAM = false>
 __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT > 200 ? CSE_ENH_MB_LARGE : CSE_ENH_MB_SMALL)) enhance_kernel(EnhanceArgs a) {
     typedef EnhanceCfg<LOG2N> C;
     constexpr int NFFT = C::NFFT, M = C::M, LOG2M = LOG2N - 1, NTB = C::NTB, PPT = C::PPT, NT = C::NT, F = C::F;
@@ -283,7 +287,7 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
     }
     __syncthreads();
     const real mu_raw = (ALG == 2) ? (real)a.params[c].v[4] : (ALG == 3) ? (real)a.params[c].v[3] : R(-1);
-    const bool smooth = (ALG >= 2) && TV && (mu_raw >= R(0));
+    const bool smooth = (ALG >= 2) && TV && !GAM && (mu_raw >= R(0));
 
     const real2* __restrict__ Yu = a.Y + (size_t)u * nf * nbp;
     const real* __restrict__ Nu = a.N + (size_t)u * (TV ? (size_t)nf * nbp : (size_t)nbp);
@@ -458,7 +462,7 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
                             const int sa = is_pair ? s : M / 2, ka = sa, kb = M - sa;
                             const real2 Ya = ytile[f * nbp + ka], Yb = ytile[f * nbp + kb];
                             const real2 Nn = TV ? mk2(ntile[f * nbp + ka], ntile[f * nbp + kb]) : mk2(nstat[i][0], nstat[i][1]);
-                            gain_pair<ALG, TV>(Ya, Yb, Nn, rstat[i], t == 0, st[i], pv, a.eps, smooth, xa, xb);
+                            gain_pair<ALG, TV, GAM>(Ya, Yb, Nn, rstat[i], t == 0, st[i], pv, a.eps, smooth, xa, xb);
                             if (sa == 0) { xa.y = R(0); xb.y = R(0); }
                             const real2 cb = mk2(xb.x, -xb.y);                     // conj X[M-s]
                             const real2 E = cadd(xa, cb), D = csub(xa, cb);
@@ -468,7 +472,7 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
                             if (sa > 0) xf[SIDX(M - sa)] = mk2(T.x, -T.y);         // conj(E) + i conj(O) = conj(E - iO)
                             continue;
                         }
-                        gain_pair<ALG, TV>(yv[i][0][f], yv[i][1][f], mk2(nv[i][0][f], nv[i][1][f]), rstat[i], t == 0, st[i], pv, a.eps, smooth, xa, xb);
+                        gain_pair<ALG, TV, GAM>(yv[i][0][f], yv[i][1][f], mk2(nv[i][0][f], nv[i][1][f]), rstat[i], t == 0, st[i], pv, a.eps, smooth, xa, xb);
                         if (!is_pair) { xf[SIDX(M / 2)] = mk2(R(2) * xa.x, R(-2) * xa.y); continue; }   // 2 conj X[M/2]
                         if (s == 0) { xf[0] = mk2(xa.x + xb.x, xa.x - xb.x); continue; }                // DC, Nyquist (real)
                         const real2 cb = mk2(xb.x, -xb.y);                     // conj X[M-s]
@@ -556,5 +560,42 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
         raddr += (unsigned)(F * hop * sizeof(real));
         while (raddr >= rend) raddr -= (unsigned)(W * sizeof(real));
         __syncthreads();
+    }
+}
+
+
+// The candidate-invariant front of the gain rules, once per (utterance, STFT shape, noise PSD, noise_mu):
+//   N'(t) = max(N(t), eps)                          (np.maximum(noise_psd, eps): wiener_filter.py:45, mmse.py:45, advanced_mmse.py:57)
+//   N'(t) = mu N'(t-1) + (1 - mu) N'(t),  t > 0       (recursive smoothing: mmse.py:48-57, advanced_mmse.py:60-66; mu < 0: none)
+//   gamma(t) = max(|Y(t)|^2 / N'(t), eps)            (a-posteriori SNR: wiener_filter.py:61, mmse.py:67, advanced_mmse.py:76)
+// One thread per (utterance, bin) walks the frames; a warp reads 32 neighbouring bins of a frame (coalesced).
+// Same operations, in the same order, as gain_pair<..., GAM = false>.
+__global__ void __launch_bounds__(128) gamma_kernel(const real2* __restrict__ Y, const real* __restrict__ N, int noise_tv, int nf,
+                                                    int nb, int nbp, real mu, real eps, real* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, u = blockIdx.y;
+    if (k >= nbp) return;
+    const real2* __restrict__ Yu = Y + (size_t)u * nf * nbp + k;
+    const real* __restrict__ Nu = N + (size_t)u * (noise_tv ? (size_t)nf * nbp : (size_t)nbp) + k;
+    real* __restrict__ o = out + (size_t)u * nf * nbp + k;
+    if (k >= nb) { for (int t = 0; t < nf; ++t) o[(size_t)t * nbp] = eps; return; }      // padding bins
+    const bool smooth = noise_tv && mu >= R(0);
+    const real one_minus_mu = R(1) - mu;
+    const real nstat = noise_tv ? R(0) : r_max(Nu[0], eps);
+    const real rstat = noise_tv ? R(0) : r_rcp(nstat);
+    real nsm = R(0);
+    for (int t = 0; t < nf; ++t) {
+        const real2 y = Yu[(size_t)t * nbp];
+        const real pw = r_fma(y.x, y.x, y.y * y.y);
+        real g;
+        if (noise_tv) {
+            real nt = r_max(Nu[(size_t)t * nbp], eps);
+            if (smooth) {
+                if (t > 0) nt = r_fma(mu, nsm, one_minus_mu * nt);
+                nsm = nt;
+                if (!CSE_GAIN_TRIM) nt = r_max(nt, eps);
+            }
+            g = pw * r_rcp(nt);
+        } else g = pw * rstat;
+        o[(size_t)t * nbp] = r_max(g, eps);
     }
 }

@@ -13,6 +13,7 @@ suite, on numpy arrays against the thread-emulated kernels.  There is no CPU com
 the product: constructing :class:`SweepEngine` without a CUDA device raises.
 """
 import ctypes
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -29,7 +30,9 @@ MAX_WAV_WORKSPACE_BYTES = 8 << 30
 #: runtime used when an engine is constructed without explicit lib/backend.  The product never
 #: changes it (-> libcse_sm100a.so + CUDA tensors); the CPU test-suite points it at the
 #: thread-emulated build to exercise the host logic without a GPU.
-_runtime = {"lib": None, "backend_factory": None, "reuse_result_buffers": False}
+_runtime = {"lib": None, "backend_factory": None, "reuse_result_buffers": False,
+            # share the candidate-invariant front of the Wiener / MMSE / Log-MMSE gain rules (cse_gamma) across a group
+            "gamma": os.environ.get("CSE_GAMMA", "1") != "0"}
 _PLAN_CACHE = OrderedDict()      # (algorithm, grid digest, frame-count signature) -> host-side launch plan, LRU
 _PLAN_CACHE_MAX = 32
 _PINNED_POOL = {}
@@ -205,6 +208,7 @@ class SweepEngine:
         self._stft = {}
         self._pow = {}
         self._noise = {}
+        self._gamma = {}
         self._ws = {}
         self._plans = {}
         self._exports = []
@@ -326,10 +330,27 @@ class SweepEngine:
         self._noise[key] = out
         return out
 
+    def gamma(self, key6):
+        """A-posteriori SNR [U][nf][nbp] for key6 = noise key + (effective noise_mu | None): ``cse_gamma`` of the
+        cached STFT and noise PSD, shared by every candidate of the group (Wiener / MMSE / Log-MMSE)."""
+        if key6 not in self._gamma:
+            key, mu = key6[:5], key6[5]
+            n_fft, hop = key[0], key[1]
+            Y = self.stft(n_fft, hop)
+            N, tv = self.noise(key)
+            be = self.be
+            G = be.empty((self.U, self.n_frames(n_fft, hop), self.lib.bins_padded(n_fft)), self.real)
+            self.lib.gamma(be.ptr(Y), be.ptr(N), int(tv), self.U, self.L, n_fft, hop, -1.0 if mu is None else float(mu),
+                           float(key[4]), be.ptr(G), be.stream())
+            self.launches += 1
+            self._gamma[key6] = G
+        return self._gamma[key6]
+
     def drop_caches(self):
         self._stft.clear()
         self._pow.clear()
         self._noise.clear()
+        self._gamma.clear()
 
     # ------------------------------------------------------------------ the sweep
     def _plan(self, alg, points):
@@ -340,7 +361,8 @@ class SweepEngine:
         sig = tuple(sorted({(int(p["n_fft"]), int(p["hop_length"]), self.n_frames(int(p["n_fft"]), int(p["hop_length"])) >= 5)
                             for p in points}))
         self._validate_shapes(points)
-        key = (alg, points_digest(points), len(points), sig)
+        split_mu = bool(_runtime.get("gamma")) and alg != _lib.ALG_SS
+        key = (alg, points_digest(points), len(points), sig, split_mu)
         pl = self._plans.get(key)
         if pl is not None:
             return pl
@@ -348,7 +370,7 @@ class SweepEngine:
         if out is not None:
             _PLAN_CACHE.move_to_end(key)
         else:
-            groups = plan(alg, points, self.n_frames)
+            groups = plan(alg, points, self.n_frames, split_mu=split_mu)
             info, col = [], 0
             for gkey, g in groups.items():
                 n_rows = len(g["rows"])
@@ -357,7 +379,7 @@ class SweepEngine:
                 info.append({"key": gkey, "rows": g["rows"], "params_host": _lib.pack_params(g["rows"]), "n_rows": n_rows,
                              "col0": col, "member_idx": member_idx, "row_idx": row_idx, "members": g["members"]})
                 col += n_rows
-            out = {"groups": info, "unique": col, "n_points": len(points)}
+            out = {"groups": info, "unique": col, "n_points": len(points), "gamma": split_mu}
             _PLAN_CACHE[key] = out
             while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
                 _PLAN_CACHE.popitem(last=False)
@@ -408,7 +430,10 @@ class SweepEngine:
             key = g["key"]
             n_fft, hop = key[0], key[1]
             Y = self.stft(n_fft, hop)
-            N, tv = self.noise(key)
+            if pl.get("gamma"):
+                N, tv = self.gamma(key), 2
+            else:
+                N, tv = self.noise(key)
             n_rows = g["n_rows"]
             pcache = pl.setdefault("params_dev", {})          # per engine: one upload per group, reused by later sweeps
             params = pcache.get(id(g))
@@ -569,7 +594,10 @@ class SweepEngine:
             key = g["key"]
             n_fft, hop = key[0], key[1]
             Y = self.stft(n_fft, hop)
-            N, tv = self.noise(key)
+            if pl.get("gamma"):
+                N, tv = self.gamma(key), 2
+            else:
+                N, tv = self.noise(key)
             uniq = sorted({(u, int(row[i])) for u, i in lst})                 # identical device candidates once
             items = np.array([u * g["n_rows"] + r for u, r in uniq], dtype=np.int32)
             params = be.from_host(g["params_host"])

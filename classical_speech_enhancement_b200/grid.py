@@ -58,12 +58,16 @@ def param_row(alg, point, noise_time_varying):
     raise ValueError(f"unknown algorithm id {alg}")
 
 
-def plan(alg, points, n_frames_of):
+def plan(alg, points, n_frames_of, split_mu=False):
     """Group grid points by the noise PSD they share and dedupe identical device candidates.
 
     Returns an ordered dict ``noise_key -> {"rows": [unique param rows], "members": [[grid
     indices sharing row r], ...]}``.  ``n_frames_of(n_fft, hop)`` tells whether the PSD is
     time-varying (the short-signal rule of ``noise_estimation.py:194-195`` makes it static).
+
+    ``split_mu``: the group key additionally carries the effective ``noise_mu`` (None where it is dead), and the
+    rows carry -1 in its place: all candidates of a group then share the smoothed PSD and with it the whole
+    candidate-invariant front of the gain rule (``cse_gamma``).
     """
     groups = OrderedDict()
     eps = alg_eps(alg)
@@ -72,6 +76,12 @@ def plan(alg, points, n_frames_of):
         n_frames = n_frames_of(key[0], key[1])
         tv = key[2] != "percentile" and n_frames >= 5
         row = param_row(alg, pt, tv)
+        if split_mu and alg != ALG_SS:
+            mu_slot = {ALG_MMSE: 4, ALG_OMLSA: 3}.get(alg)
+            mu = row[mu_slot] if mu_slot is not None else -1.0
+            key = key + (mu if mu >= 0 else None,)
+            if mu_slot is not None:
+                row = row[:mu_slot] + (-1.0,) + row[mu_slot + 1:]
         g = groups.setdefault(key, {"rows": [], "members": [], "index": {}, "time_varying": tv})
         r = g["index"].get(row)
         if r is None:

@@ -110,8 +110,17 @@ int cse_noise_percentile(const void* P, int n_utts, int n_frames, int n_fft, dou
 int cse_noise_mintrack(const void* P, int n_utts, int n_frames, int n_fft, double eps, void* N,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* The candidate-invariant front of the Wiener / MMSE / Log-MMSE gain rules, once per (utterance, shape, noise PSD,
+ * noise_mu): gamma[u][t][k] = max(|Y|^2 / N', eps), N' = max(N, eps) smoothed recursively over the frames with noise_mu
+ * when noise_mu >= 0 and the PSD is time-varying (Code/wiener_filter.py:45,61, mmse.py:45-57,67,
+ * advanced_mmse.py:57-66,76).  N as for cse_enhance (noise_tv 0 / 1); G [U][nf][nbp].  cse_enhance* take G in place
+ * of N with noise_tv = 2 (and ignore the candidates' noise_mu): hundreds of candidates then share this work. */
+int cse_gamma(const void* Y, const void* N, int noise_tv, int n_utts, int length, int n_fft, int hop,
+              double noise_mu, double eps, void* G, void* stream);
+
 /* Gain + ISTFT for n_utts x n_params candidates (utterance-major): out[(u*n_params+c)][L].
- * noise_tv: 0 -> N is [U][nbp] (static), 1 -> N is [U][nf][nbp] (time-varying).
+ * noise_tv: 0 -> N is [U][nbp] (static), 1 -> N is [U][nf][nbp] (time-varying), 2 -> N is the a-posteriori SNR
+ * [U][nf][nbp] of cse_gamma (algorithms WIENER, MMSE, OMLSA only).
  * eps: the algorithm's epsilon (1e-10; 1e-12 for MMSE, Code/mmse.py:17).
  * Replaces the body of the four reference entry points after their STFT / noise_estimation
  * calls, including librosa.istft(..., length=L). */
