@@ -442,8 +442,13 @@ class SweepEngine:
             keep.append(params)
             sc_ptr = be.ptr_at(uniq, self.U * g["col0"] * rec)          # group block [U][n_rows]
             total = self.U * n_rows
-            chunk = min(self.chunk_items, total)
             rb = np.dtype(self.real).itemsize
+            # near-equal chunks, as many as the total rounds to: a group of 1.04 chunks runs as ONE launch (a few
+            # hundred candidates launched on their own would cost two waves of the whole GPU), never more than 1.5 chunks
+            n_chunks = max(1, int(total / self.chunk_items + 0.5))
+            chunk = -(-total // n_chunks)
+            if chunk * self.L * rb > MAX_WAV_WORKSPACE_BYTES:
+                chunk = min(self.chunk_items, total)
             wavs = [self._workspace("wav", chunk * self.L * rb)]
             if chunk_sink is not None:
                 wavs.append(self._workspace("wav1", chunk * self.L * rb))
