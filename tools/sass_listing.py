@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 prefix = sys.argv[1] if len(sys.argv) > 1 else "r02"
 lib = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, "classical_speech_enhancement_b200", "libcse_sm100a.so")
 raw = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-want = {"_Z14enhance_kernelILi3ELi10ELb1ELb1EEv11EnhanceArgs": "enhance_kernel_3_10_staged_tv",
+want = {"_Z14enhance_kernelILi3ELi10ELb1ELb1ELb1EEv11EnhanceArgs": "enhance_kernel_3_10_staged_gamma",
         "_Z18select_best_kernelPK11cse_score_tPKdiP12cse_winner_t": "select_best_kernel",
         "_Z18stoi_stream_kernel9ScoreArgs": "stoi_stream_kernel",
         "_Z12align_kernelILb0EEv9ScoreArgs": "align_kernel_0"}
