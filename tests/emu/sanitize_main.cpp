@@ -80,6 +80,20 @@ static int run_case(int L, int nan_at) {
                 std::vector<cse_winner_t> win((size_t)U * 3);
                 const double pesq[6] = {2.0, 2.5, (double)NAN, 1.0, 3.0, 3.0004};
                 CHECK(cse_select_best(nominal.data(), pesq, U, 3, win.data(), nullptr));
+                if (alg >= 1) {      // the shared front: gamma in place of the PSD (noise_tv = 2) must give the same scores
+                    std::vector<real> G((size_t)U * nf * nbp);
+                    std::vector<cse_score_t> scores2((size_t)U * n_params);
+                    const double mu = (alg == 2) ? rows[alg][0].v[4] : (alg == 3 ? rows[alg][0].v[3] : -1.0);
+                    CHECK(cse_gamma(Y.data(), nz.N, nz.tv, U, L, n_fft, hop, nz.tv ? mu : -1.0, alg == 2 ? 1e-12 : 1e-10, G.data(), nullptr));
+                    CHECK(cse_sweep(tables.data(), alg, Y.data(), G.data(), 2, U, L, n_fft, hop, rows[alg], 1, sr, clean.data(),
+                                    cache.data(), scores2.data(), chunk, ws.data(), ws.size(), nullptr));
+                    for (int u = 0; u < U; ++u)
+                        if ((scores2[u].flags & CSE_FLAG_VALID) != (scores[(size_t)u * n_params].flags & CSE_FLAG_VALID) ||
+                            ((scores2[u].flags & CSE_FLAG_VALID) && fabs((double)scores2[u].stoi - (double)scores[(size_t)u * n_params].stoi) > 1e-5)) {
+                            fprintf(stderr, "gamma path differs: alg %d u %d: %g vs %g\n", alg, u, (double)scores2[u].stoi, (double)scores[(size_t)u * n_params].stoi);
+                            return 1;
+                        }
+                }
                 const int items[2] = {3, 0};
                 std::vector<real> out((size_t)2 * L);
                 CHECK(cse_enhance_list(tables.data(), alg, Y.data(), nz.N, nz.tv, L, n_fft, hop, rows[alg], n_params, items, 2,
