@@ -5,9 +5,12 @@ utterance-configs/s at 1/2/4/8 B200, plus achieved HBM GB/s against the measured
 One "step" = one pass of the whole hot path over the whole synthetic test set: for every
 utterance pair, all four algorithms x the full ``parameter_ranges.py`` grids (9744 nominal /
 5004 unique grid points): STFTs, noise PSDs, clean-side scoring caches, gain + ISTFT,
-alignment, STOI and SNR for every candidate.  With N GPUs the utterances are sharded in
-contiguous blocks (strong scaling: the job is fixed at --utts utterances) and the score tables
-are all-gathered over NCCL at the end of the step.
+alignment, STOI and SNR for every candidate, and the reference's three-way selection scan per
+(utterance, algorithm) on the device.  With N GPUs the utterances are sharded in contiguous blocks
+(strong scaling: the job is fixed at --utts utterances), every rank selects for its own utterances
+and the winners' records are all-gathered over NCCL at the end of the step.  The line also carries
+its own checks: oracle parity of sampled table entries, device-vs-host selection, checksums that
+must be equal at every N.
 
     python bench.py --gpus 1 --steps 3 --warmup 3
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
