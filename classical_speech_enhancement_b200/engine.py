@@ -368,7 +368,10 @@ class SweepEngine:
             return pl
         out = _PLAN_CACHE.get(key)
         if out is not None:
-            _PLAN_CACHE.move_to_end(key)
+            try:
+                _PLAN_CACHE.move_to_end(key)
+            except KeyError:            # evicted by another host thread in between: the plan in hand stays valid
+                pass
         else:
             groups = plan(alg, points, self.n_frames, split_mu=split_mu)
             info, col = [], 0
@@ -382,7 +385,10 @@ class SweepEngine:
             out = {"groups": info, "unique": col, "n_points": len(points), "gamma": split_mu}
             _PLAN_CACHE[key] = out
             while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
-                _PLAN_CACHE.popitem(last=False)
+                try:
+                    _PLAN_CACHE.popitem(last=False)
+                except KeyError:
+                    break
         pl = dict(out)
         self._plans[key] = pl
         return pl
