@@ -368,10 +368,7 @@ class SweepEngine:
             return pl
         out = _PLAN_CACHE.get(key)
         if out is not None:
-            try:
-                _PLAN_CACHE.move_to_end(key)
-            except KeyError:            # evicted by another host thread in between: the plan in hand stays valid
-                pass
+            _PLAN_CACHE.move_to_end(key)
         else:
             groups = plan(alg, points, self.n_frames, split_mu=split_mu)
             info, col = [], 0
@@ -385,10 +382,7 @@ class SweepEngine:
             out = {"groups": info, "unique": col, "n_points": len(points), "gamma": split_mu}
             _PLAN_CACHE[key] = out
             while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
-                try:
-                    _PLAN_CACHE.popitem(last=False)
-                except KeyError:
-                    break
+                _PLAN_CACHE.popitem(last=False)
         pl = dict(out)
         self._plans[key] = pl
         return pl

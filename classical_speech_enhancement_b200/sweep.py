@@ -178,16 +178,10 @@ def sweep_dataset(clean, noisy, grids=DEFAULT_GRIDS, sr=16000, select=True, chun
 
 
 def sweep_pairs(pairs, grids=DEFAULT_GRIDS, sr=16000, select=True, chunk_items=DEFAULT_CHUNK_ITEMS, engine_kwargs=None,
-                tables=True, streams=1):
+                tables=True):
     """Variable-length form of :func:`sweep_dataset`: ``pairs`` is a list of (clean, noisy) 1-D arrays
     (each pair equal length, pair-aligned, 16 kHz).  Pairs are bucketed by length - one engine (and
-    one set of cached spectrograms) per distinct length - and results are returned in input order.
-
-    Real corpora have almost as many lengths as utterances, and a bucket of one utterance launches grids far
-    smaller than the GPU (a 144-candidate group on 148 SMs).  ``streams`` > 1 runs that many buckets at a time,
-    each on its own CUDA stream from its own host thread (the C ABI takes the stream per call and keeps no global
-    state; ctypes releases the GIL), so that the small kernels of different buckets fill the device together.
-    Every bucket's result is the same as with ``streams=1``."""
+    one set of cached spectrograms) per distinct length - and results are returned in input order."""
     by_len = {}
     for i, (c, n) in enumerate(pairs):
         c = np.asarray(c)
@@ -195,46 +189,24 @@ def sweep_pairs(pairs, grids=DEFAULT_GRIDS, sr=16000, select=True, chunk_items=D
         if c.ndim != 1 or c.shape != n.shape:
             raise ValueError(f"pair {i}: clean and noisy must be 1-D arrays of equal length")
         by_len.setdefault(len(c), []).append(i)
-
-    def one_bucket(idx):
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
+    scores, winners, points, nominal, unique = None, None, None, 0, 0
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for L, idx in sorted(by_len.items()):
             out = sweep_dataset(np.stack([pairs[i][0] for i in idx]), np.stack([pairs[i][1] for i in idx]), grids=grids,
                                 sr=sr, select=select, chunk_items=chunk_items, engine_kwargs=engine_kwargs, tables=tables)
-        out.pop("engine", None)                     # device buffers go back to the allocator with the bucket
-        return out
-
-    buckets = [idx for _, idx in sorted(by_len.items())]
-    if streams > 1 and len(buckets) > 1:
-        import torch
-        from concurrent.futures import ThreadPoolExecutor
-        one_bucket(buckets[0][:1])                  # plans, constant tables and kernel attributes are set up once, up front
-
-        def on_stream(idx):
-            stream = torch.cuda.Stream()
-            with torch.cuda.stream(stream):
-                out = one_bucket(idx)
-                stream.synchronize()
-            return out
-        with ThreadPoolExecutor(int(streams)) as ex:
-            outs = list(ex.map(on_stream, buckets))
-    else:
-        outs = [one_bucket(idx) for idx in buckets]
-
-    scores, winners, points, nominal, unique = None, None, None, 0, 0
-    for idx, out in zip(buckets, outs):
-        points = out["points"]
-        if tables:
-            if scores is None:
-                scores = {name: np.zeros((len(pairs), sc.shape[1]), dtype=sc.dtype) for name, sc in out["scores"].items()}
-            for name, sc in out["scores"].items():
-                scores[name][idx] = sc
-        if select:
-            if winners is None:
-                winners = {name: np.zeros((len(pairs), 3), dtype=w.dtype) for name, w in out["winners"].items()}
-            for name, w in out["winners"].items():
-                winners[name][idx] = w
-        nominal += out["nominal"]
-        unique += out["unique"]
+            points = out["points"]
+            if tables:
+                if scores is None:
+                    scores = {name: np.zeros((len(pairs), sc.shape[1]), dtype=sc.dtype) for name, sc in out["scores"].items()}
+                for name, sc in out["scores"].items():
+                    scores[name][idx] = sc
+            if select:
+                if winners is None:
+                    winners = {name: np.zeros((len(pairs), 3), dtype=w.dtype) for name, w in out["winners"].items()}
+                for name, w in out["winners"].items():
+                    winners[name][idx] = w
+            nominal += out["nominal"]
+            unique += out["unique"]
     return {"scores": scores, "points": points, "nominal": nominal, "unique": unique, "winners": winners,
             "selection": selection_from_winners(points, winners, False) if select else None}

@@ -299,25 +299,3 @@ def test_run_dataset_on_device_files_and_resume(tmp_path):
     rows2, summary2 = run_dataset(pairs, out_dirs, str(tmp_path / "summary"), algorithms=algorithms, pesq_scorer=_corr_pesq,
                                   pesq_workers=4, verbose=False)
     assert rows2[:12] == saved and len(rows2) == 16 and summary2["omlsa"]["count"] == 4
-
-
-def test_variable_length_buckets_on_concurrent_streams():
-    """Real corpora have as many lengths as utterances: buckets of one utterance run on several CUDA streams at a
-    time (one host thread each) so that their small launches fill the device together - same tables, same winners."""
-    import time
-    import torch
-    from classical_speech_enhancement_b200.sweep import sweep_pairs
-    lengths = [32000, 33117, 35000, 36250, 38000, 40001, 41000, 43333, 32000, 35000, 45000, 47999]
-    pairs = [tuple(f32(x) for x in make_pair(700 + i, L)) for i, L in enumerate(lengths)]
-    grids = (("wiener", pr.param_ranges_wiener), ("spectralSubtractor", pr.param_ranges_ss))
-    sweep_pairs(pairs[:2], grids=grids)                                  # warm-up
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    seq = sweep_pairs(pairs, grids=grids)
-    t1 = time.perf_counter()
-    par = sweep_pairs(pairs, grids=grids, streams=4)
-    t2 = time.perf_counter()
-    for name, _ in grids:
-        assert np.array_equal(seq["scores"][name], par["scores"][name])
-        assert np.array_equal(seq["winners"][name], par["winners"][name])
-    print(f"12 pairs / 10 lengths: sequential {1e3 * (t1 - t0):.0f} ms, 4 streams {1e3 * (t2 - t1):.0f} ms")
