@@ -42,7 +42,18 @@ _TABLES_CACHE = {}               # (library, device) -> constant tables buffer (
 class GridPoints(list):
     """A grid's point list that remembers its content digest (see :func:`points_digest`); what
     ``sweep.cached_points`` hands out so that repeated sweeps of the same grid skip re-hashing it."""
-    __slots__ = ("_cse_digest",)
+    __slots__ = ("_cse_digest", "_cse_shapes")
+
+
+def points_shapes(points):
+    """The distinct (n_fft, hop_length, noise_method) triples of a grid (what validation and the frame-count
+    signature of a plan depend on) - remembered on a :class:`GridPoints`."""
+    sh = getattr(points, "_cse_shapes", None)
+    if sh is None:
+        sh = sorted({(int(p["n_fft"]), int(p["hop_length"]), p.get("noise_method")) for p in points}, key=str)
+        if isinstance(points, GridPoints):
+            points._cse_shapes = sh
+    return sh
 
 
 def points_digest(points):
@@ -358,8 +369,7 @@ class SweepEngine:
         process through a bounded LRU keyed by the grid's CONTENT (algorithm, digest of the points, which shapes
         are time-varying) - never by object identity, so a rebuilt or edited point list can neither leak nor hit
         a stale plan; device-side maps / parameter uploads live in the per-engine copy."""
-        sig = tuple(sorted({(int(p["n_fft"]), int(p["hop_length"]), self.n_frames(int(p["n_fft"]), int(p["hop_length"])) >= 5)
-                            for p in points}))
+        sig = tuple(sorted({(n_fft, hop, self.n_frames(n_fft, hop) >= 5) for n_fft, hop, _ in points_shapes(points)}))
         self._validate_shapes(points)
         split_mu = bool(_runtime.get("gamma")) and alg != _lib.ALG_SS
         key = (alg, points_digest(points), len(points), sig, split_mu)
@@ -390,12 +400,7 @@ class SweepEngine:
     def _validate_shapes(self, points):
         """The build's operating range (include/cse.h), checked once per grid with a message that names the
         offending point instead of failing in the middle of a sweep."""
-        seen = set()
-        for p in points:
-            k = (int(p["n_fft"]), int(p["hop_length"]), p.get("noise_method"))
-            if k in seen:
-                continue
-            seen.add(k)
+        for k in points_shapes(points):
             n_fft, hop, method = k
             if n_fft not in (256, 512, 1024, 2048):
                 raise _lib.CseError(_lib.CSE_EINVAL, f"n_fft {n_fft} not in {{256,512,1024,2048}}")
@@ -623,8 +628,11 @@ class SweepEngine:
         U, C, L = wav.shape
         if U != self.U or L != self.L:
             raise ValueError("waveforms must be [U, C, L] for this batch")
+        return self._score_device(self.be.from_host(wav), C, finalize)
+
+    def _score_device(self, dev, C, finalize):
         be, lib_ = self.be, self.lib
-        dev = be.from_host(wav)
+        U, L = self.U, self.L
         scores = be.empty((U * C * self.lib.score_dtype.itemsize,), np.uint8)
         nbytes = lib_.score_workspace_bytes(U * C, L, SR)
         ws = self._workspace("score", nbytes)
@@ -634,8 +642,9 @@ class SweepEngine:
         return be.view_bytes_as(scores, self.lib.score_dtype).reshape(U, C)
 
     def baseline(self):
-        """STOI / SNR of the unprocessed noisy signals (``optimize_parameters`` ``:116-118``)."""
-        return self.score_waveforms(self.be.to_host(self.noisy)[:, None, :], finalize=False)[:, 0]
+        """STOI / SNR of the unprocessed noisy signals (``optimize_parameters`` ``:116-118``), scored where they
+        already are: on the device."""
+        return self._score_device(self.noisy, 1, False)[:, 0]
 
     def noise_psd_host(self, method, n_fft, hop, percentile, eps):
         """(bins, 1) or (bins, frames) float64 per utterance, reference orientation."""

@@ -216,7 +216,8 @@ def optimize_parameters(clean_reference, noisy_audio, sr, algorithm_function, pa
     clean = np.asarray(clean_reference, dtype=np.float64)
     noisy = np.asarray(noisy_audio, dtype=np.float64)
     eng = engine if engine is not None else SweepEngine(clean[None, :], noisy[None, :], sr=sr)
-    points = grid_points(param_ranges)
+    from .sweep import cached_points
+    points = cached_points(alg_name or "custom", param_ranges)     # the grid and its launch plan are reused from pair to pair
     if verbose:
         print(f"\n{'=' * 60}\nParameter Optimization\n{'=' * 60}")
         print(f"Testing {len(points)} parameter combinations")

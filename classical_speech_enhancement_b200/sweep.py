@@ -32,18 +32,20 @@ def nominal_and_unique(grids=DEFAULT_GRIDS):
 _points_cache = {}
 
 
-def cached_points(name, ranges):
-    """grid_points(ranges), cached per (algorithm, ranges object) so that engines can reuse their launch plans."""
-    key = (name, id(ranges))
-    hit = _points_cache.get(key)
-    if hit is None or hit[0] is not ranges or hit[2] != _ranges_signature(ranges):
-        hit = (ranges, GridPoints(grid_points(ranges)), _ranges_signature(ranges))
-        _points_cache[key] = hit
-    return hit[1]
-
-
 def _ranges_signature(ranges):
     return tuple((k, tuple(v)) for k, v in ranges.items())
+
+
+def cached_points(name, ranges):
+    """grid_points(ranges) as a :class:`GridPoints`, cached by the CONTENT of the range dict (bounded), so that engines
+    reuse launch plans and the per-pair entry points do not re-enumerate and re-hash a grid for every pair."""
+    key = (name, _ranges_signature(ranges))
+    hit = _points_cache.get(key)
+    if hit is None:
+        if len(_points_cache) >= 64:
+            _points_cache.pop(next(iter(_points_cache)))
+        hit = _points_cache[key] = GridPoints(grid_points(ranges))
+    return hit
 
 
 def run_engine_device(engine, grids=DEFAULT_GRIDS, u_pad=None):
