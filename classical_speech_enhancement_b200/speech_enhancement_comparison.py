@@ -128,6 +128,25 @@ def finalize_enhanced(enhanced, clean_ref, sr, do_align=True):
     return finalize_host(enhanced, int(sc["lag"]), len(clean_ref))
 
 
+_last_engine = {"key": None, "engine": None}
+
+
+def _engine_for_pair(clean, noisy, sr):
+    """The reference's ``main`` calls ``run_algorithm_on_pair`` four times per pair (``:447-455``), one algorithm each:
+    the engine of the most recent pair - waveforms on the device, clean-side scoring caches, STFTs, noise PSDs - is kept
+    and reused when the SAME samples come back (content checksum, not object identity), so only the first of the
+    four calls pays for them."""
+    import zlib
+    from . import engine as _engine
+    key = (sr, clean.shape, noisy.shape, zlib.crc32(clean.tobytes()), zlib.crc32(noisy.tobytes()),
+           id(_engine._runtime["lib"]), id(_engine._runtime["backend_factory"]), bool(_engine._runtime.get("gamma")))
+    if _last_engine["key"] != key:
+        _last_engine["engine"] = None                      # release the previous pair's buffers first
+        _last_engine["engine"] = SweepEngine(clean[None, :], noisy[None, :], sr=sr)
+        _last_engine["key"] = key
+    return _last_engine["engine"]
+
+
 def _resolve_algorithm(algorithm_function, _depth=0):
     """Which of the four device algorithms a callable stands for, or None.
 
@@ -215,7 +234,7 @@ def optimize_parameters(clean_reference, noisy_audio, sr, algorithm_function, pa
     alg_name = _resolve_algorithm(algorithm_function)
     clean = np.asarray(clean_reference, dtype=np.float64)
     noisy = np.asarray(noisy_audio, dtype=np.float64)
-    eng = engine if engine is not None else SweepEngine(clean[None, :], noisy[None, :], sr=sr)
+    eng = engine if engine is not None else _engine_for_pair(clean, noisy, sr)
     from .sweep import cached_points
     points = cached_points(alg_name or "custom", param_ranges)     # the grid and its launch plan are reused from pair to pair
     if verbose:
