@@ -10,9 +10,11 @@ points per (utterance, algorithm) - are re-materialised, by one sparse ``cse_enh
 group, finalized with the lag the device estimated and written out.  Same files, same row keys, same resume
 semantics.
 """
+import contextlib
 import json
 import os
 import re
+import time
 import warnings
 
 import numpy as np
@@ -85,7 +87,7 @@ def _prepare(pair, target_sr):
 
 
 def run_dataset(pairs, out_dirs, summary_dir, *, algorithms=None, resume=False, start_from="", pesq_scorer="auto",
-                pesq_workers=None, target_sr=16000, write_wavs=True, verbose=True):
+                pesq_workers=None, target_sr=16000, write_wavs=True, verbose=True, in_flight=8, checkpoint_seconds=2.0):
     """The reference's batch run over ``pairs`` ([{"stem", "clean", "noisy"}], paths or arrays; arrays already at
     16 kHz and pair-aligned may carry ``"prepared": True``).
 
@@ -93,6 +95,8 @@ def run_dataset(pairs, out_dirs, summary_dir, *, algorithms=None, resume=False, 
     ``summary_dir`` receives ``all_results.json`` (also the resume record: (stem, algorithm) rows found there are
     skipped, ``:451-453``), ``summary_means.json`` and ``all_results.csv``.  ``resume=True`` additionally skips
     stems whose winner WAVs exist (``--resume``), ``start_from`` skips everything before that stem (``--start-from``).
+    ``in_flight``: length buckets enqueued side by side (PESQ-free runs); ``checkpoint_seconds``: how often at most
+    ``all_results.json`` is rewritten while running.
     Returns (all_results, summary)."""
     from .speech_enhancement_comparison import algorithms_table, write_wav_pcm16
     algorithms = algorithms or algorithms_table()
@@ -104,6 +108,8 @@ def run_dataset(pairs, out_dirs, summary_dir, *, algorithms=None, resume=False, 
             all_results = json.load(f)
     have = {(r.get("stem"), r.get("alg")) for r in all_results}
     pairs = list(pairs)
+    n_before = len(all_results)
+    input_order = {p["stem"]: i for i, p in enumerate(pairs)}
     if resume:
         done = processed_stems(out_dirs.values())
         pairs = [p for p in pairs if p["stem"] not in done]
@@ -127,58 +133,111 @@ def run_dataset(pairs, out_dirs, summary_dir, *, algorithms=None, resume=False, 
     for p in todo:
         buckets.setdefault(len(prepared[p["stem"]][0]), []).append(p["stem"])
 
-    for L, stems in sorted(buckets.items()):
-        clean = np.stack([prepared[s][0] for s in stems])
-        noisy = np.stack([prepared[s][1] for s in stems])
-        chunk = PESQ_CHUNK_ITEMS if scorer is not None else None
-        eng = SweepEngine(clean, noisy, sr=target_sr, **({"chunk_items": chunk} if chunk else {}))
-        base = eng.baseline()
-        base_pesq = [None] * len(stems)
-        if scorer is not None:
-            from .pesq_pool import PesqPool
-            with PesqPool(scorer, target_sr, workers=pesq_workers) as pool:
-                for u in range(len(stems)):
-                    pool.submit(u, [0], clean[u], [noisy[u]])
-                tab = pool.table(len(stems), 1)
-            base_pesq = [None if np.isnan(v) else float(v) for v in tab[:, 0]]
-        rows_by_stem = {s: [] for s in stems}
-        for alg_name, _fn, ranges, *_ in algorithms:
-            need = [u for u, s in enumerate(stems) if (s, alg_name) not in have]
-            if not need:
-                continue
-            grids = ((alg_name, ranges),)
+    streams = [None]
+    if scorer is None and in_flight > 1 and len(buckets) > 1:
+        from .sweep import _bucket_streams, _engine_runtime_is_emulated
+        if not _engine_runtime_is_emulated():
+            streams = _bucket_streams(int(in_flight))
+
+    def on(stream):
+        if stream is None:
+            return contextlib.nullcontext()
+        import torch
+        return torch.cuda.stream(stream)
+
+    def start(L, stems, stream):
+        """Everything of a bucket that only ENQUEUES device work: engine, baseline scores, the sweeps and the
+        selection of every algorithm still needed (with PESQ the sweep itself waits for the pool, chunk by chunk)."""
+        with on(stream):
+            clean = np.stack([prepared[s][0] for s in stems])
+            noisy = np.stack([prepared[s][1] for s in stems])
+            chunk = PESQ_CHUNK_ITEMS if scorer is not None else None
+            eng = SweepEngine(clean, noisy, sr=target_sr, **({"chunk_items": chunk} if chunk else {}))
+            base = eng.baseline_device()
+            base_pesq = [None] * len(stems)
             if scorer is not None:
-                items, pesq = run_engine_device_with_pesq(eng, scorer, grids, pesq_workers=pesq_workers)
-            else:
-                items, pesq = run_engine_device(eng, grids), None
-            pts = cached_points(alg_name, ranges)
-            win = eng.winners_to_host(select_winners_device(eng, items, pesq)[alg_name]).copy()
-            best = [best_from_winners(pts, win[u], pesq_available=scorer is not None) for u in range(len(stems))]
-            wanted = sorted({(u, b[c]["index"]) for u in need for b in (best[u],) for c, _ in WAV_TAGS if b[c]["index"] is not None})
-            raw = eng.enhance_list(alg_name, pts, wanted) if (write_wavs and wanted) else {}
-            for u in need:
-                stem, b = stems[u], best[u]
-                if b["stoi"]["index"] is None:
-                    if verbose:
-                        print(f" {stem} / {alg_name}: no valid parameters found")     # the reference raises here (:233-235)
+                from .pesq_pool import PesqPool
+                with PesqPool(scorer, target_sr, workers=pesq_workers) as pool:
+                    for u in range(len(stems)):
+                        pool.submit(u, [0], clean[u], [noisy[u]])
+                    tab = pool.table(len(stems), 1)
+                base_pesq = [None if np.isnan(v) else float(v) for v in tab[:, 0]]
+            swept = []
+            for alg_name, _fn, ranges, *_ in algorithms:
+                need = [u for u, s in enumerate(stems) if (s, alg_name) not in have]
+                if not need:
                     continue
-                if write_wavs:
-                    os.makedirs(out_dirs[alg_name], exist_ok=True)
-                    for crit, tag in WAV_TAGS:
-                        if b[crit]["index"] is None:
-                            continue
-                        wav = finalize_host(raw[(u, b[crit]["index"])], b[crit]["lag"], L)
-                        write_wav_pcm16(os.path.join(out_dirs[alg_name], f"{stem}_{alg_name}_optimized_{tag}.wav"), wav, target_sr)
-                baseline = {"stoi": float(base[u]["stoi"]) or 0, "pesq": base_pesq[u] if scorer is not None else None,
-                            "snr": (float("inf") if base[u]["flags"] & 4 else float(base[u]["snr"])) or 0}
-                rows_by_stem[stem].append(results_io.result_row(alg_name, stem, target_sr, baseline, b))
-        for s in stems:                                       # the reference appends and rewrites the JSON per pair (:455-458)
+                grids = ((alg_name, ranges),)
+                if scorer is not None:
+                    items, pesq = run_engine_device_with_pesq(eng, scorer, grids, pesq_workers=pesq_workers)
+                else:
+                    items, pesq = run_engine_device(eng, grids), None
+                swept.append((alg_name, ranges, need, select_winners_device(eng, items, pesq)[alg_name]))
+        return L, stems, stream, eng, base, base_pesq, swept
+
+    def finish(job):
+        """Winners to the host, their waveforms re-materialised and written, the rows appended."""
+        L, stems, stream, eng, base, base_pesq, swept = job
+        rows_by_stem = {s: [] for s in stems}
+        with on(stream):
+            base = eng.scores_to_host(base, 1)[:, 0]
+            for alg_name, ranges, need, dev_win in swept:
+                pts = cached_points(alg_name, ranges)
+                win = eng.winners_to_host(dev_win).copy()
+                best = [best_from_winners(pts, win[u], pesq_available=scorer is not None) for u in range(len(stems))]
+                wanted = sorted({(u, b[c]["index"]) for u in need for b in (best[u],) for c, _ in WAV_TAGS if b[c]["index"] is not None})
+                raw = eng.enhance_list(alg_name, pts, wanted) if (write_wavs and wanted) else {}
+                for u in need:
+                    stem, b = stems[u], best[u]
+                    if b["stoi"]["index"] is None:
+                        if verbose:
+                            print(f" {stem} / {alg_name}: no valid parameters found")     # the reference raises here (:233-235)
+                        continue
+                    if write_wavs:
+                        os.makedirs(out_dirs[alg_name], exist_ok=True)
+                        for crit, tag in WAV_TAGS:
+                            if b[crit]["index"] is None:
+                                continue
+                            wav = finalize_host(raw[(u, b[crit]["index"])], b[crit]["lag"], L)
+                            write_wav_pcm16(os.path.join(out_dirs[alg_name], f"{stem}_{alg_name}_optimized_{tag}.wav"), wav, target_sr)
+                    baseline = {"stoi": float(base[u]["stoi"]) or 0, "pesq": base_pesq[u] if scorer is not None else None,
+                                "snr": (float("inf") if base[u]["flags"] & 4 else float(base[u]["snr"])) or 0}
+                    rows_by_stem[stem].append(results_io.result_row(alg_name, stem, target_sr, baseline, b))
+        for s in stems:
             all_results.extend(rows_by_stem[s])
             have.update((s, r["alg"]) for r in rows_by_stem[s])
-        with open(json_path, "w", encoding="utf-8") as f:
-            json.dump(all_results, f, indent=2, ensure_ascii=False)
+        checkpoint()
         if verbose:
             print(f"bucket of {len(stems)} pairs x {L} samples done ({len(all_results)} rows so far)")
+
+    last_write = [time.monotonic()]
+
+    def checkpoint(force=False):
+        """The reference rewrites the whole JSON after every pair (:455-458) - quadratic in the corpus and, at a few
+        milliseconds of device work per pair, the dominant cost.  Here: at most every ``checkpoint_seconds``, and at
+        the end; an interrupted run loses at most that much work."""
+        if not force and time.monotonic() - last_write[0] < checkpoint_seconds:
+            return
+        tmp = json_path + ".part"
+        with open(tmp, "w", encoding="utf-8") as f:
+            json.dump(all_results, f, indent=2, ensure_ascii=False)
+        os.replace(tmp, json_path)
+        last_write[0] = time.monotonic()
+
+    # longest bucket first (the caching allocator's blocks then fit every later bucket); without PESQ up to
+    # ``in_flight`` buckets are enqueued, each on its own stream, before the oldest is read back (sweep.sweep_pairs)
+    pending = []
+    try:
+        for k, (L, stems) in enumerate(sorted(buckets.items(), reverse=True)):
+            if len(pending) >= len(streams):
+                finish(pending.pop(0))
+            pending.append(start(L, stems, streams[k % len(streams)]))
+        while pending:
+            finish(pending.pop(0))
+    finally:
+        # rows of this run in the order the pairs were given (the reference's loop order), whatever the bucket order
+        all_results[n_before:] = sorted(all_results[n_before:], key=lambda r: input_order.get(r["stem"], -1))
+        checkpoint(force=True)
 
     summary = results_io.write_results(all_results, [a[0] for a in algorithms], summary_dir)
     return all_results, summary

@@ -631,6 +631,12 @@ class SweepEngine:
         return self._score_device(self.be.from_host(wav), C, finalize)
 
     def _score_device(self, dev, C, finalize):
+        return self.scores_to_host(self._score_enqueue(dev, C, finalize), C)
+
+    def scores_to_host(self, scores, C):
+        return self.be.view_bytes_as(scores, self.lib.score_dtype).reshape(self.U, C)
+
+    def _score_enqueue(self, dev, C, finalize):
         be, lib_ = self.be, self.lib
         U, L = self.U, self.L
         scores = be.empty((U * C * self.lib.score_dtype.itemsize,), np.uint8)
@@ -639,7 +645,11 @@ class SweepEngine:
         lib_.score(be.ptr(self.tables), be.ptr(dev), U, C, L, SR, be.ptr(self.clean), be.ptr(self.cache),
                    int(finalize), be.ptr(scores), be.ptr(ws), nbytes, be.stream())
         self.launches += 2
-        return be.view_bytes_as(scores, self.lib.score_dtype).reshape(U, C)
+        return scores
+
+    def baseline_device(self):
+        """:meth:`baseline` without the read-back: the device buffer, for :meth:`scores_to_host` (…, 1)[:, 0]."""
+        return self._score_enqueue(self.noisy, 1, False)
 
     def baseline(self):
         """STOI / SNR of the unprocessed noisy signals (``optimize_parameters`` ``:116-118``), scored where they

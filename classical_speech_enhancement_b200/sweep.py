@@ -180,10 +180,15 @@ def sweep_dataset(clean, noisy, grids=DEFAULT_GRIDS, sr=16000, select=True, chun
 
 
 def sweep_pairs(pairs, grids=DEFAULT_GRIDS, sr=16000, select=True, chunk_items=DEFAULT_CHUNK_ITEMS, engine_kwargs=None,
-                tables=True):
+                tables=True, in_flight=8):
     """Variable-length form of :func:`sweep_dataset`: ``pairs`` is a list of (clean, noisy) 1-D arrays
     (each pair equal length, pair-aligned, 16 kHz).  Pairs are bucketed by length - one engine (and
-    one set of cached spectrograms) per distinct length - and results are returned in input order."""
+    one set of cached spectrograms) per distinct length - and results are returned in input order.
+
+    A real corpus has almost as many lengths as utterances, and a bucket of one utterance launches grids far smaller
+    than the GPU (a 144-candidate group on 148 SMs).  Up to ``in_flight`` buckets are therefore enqueued - each on its
+    own CUDA stream, from this one host thread, nothing synchronised - before the oldest one's results are read back,
+    so that the small kernels of neighbouring buckets run side by side.  Results do not depend on ``in_flight``."""
     by_len = {}
     for i, (c, n) in enumerate(pairs):
         c = np.asarray(c)
@@ -191,24 +196,79 @@ def sweep_pairs(pairs, grids=DEFAULT_GRIDS, sr=16000, select=True, chunk_items=D
         if c.ndim != 1 or c.shape != n.shape:
             raise ValueError(f"pair {i}: clean and noisy must be 1-D arrays of equal length")
         by_len.setdefault(len(c), []).append(i)
+    # longest first: every later bucket fits the blocks the caching allocator already holds (ascending order would
+    # ask for a slightly larger block each time - a cudaMalloc, and its device-wide synchronisation, per bucket)
+    buckets = [idx for _, idx in sorted(by_len.items(), reverse=True)]
+    try:
+        import torch
+        use_streams = in_flight > 1 and len(buckets) > 1 and torch.cuda.is_available() and not _engine_runtime_is_emulated()
+    except ImportError:
+        use_streams = False
+
+    import contextlib
+
+    def on(stream):
+        return torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+
+    def enqueue(idx, stream):
+        with on(stream):
+            eng = SweepEngine(np.stack([pairs[i][0] for i in idx]), np.stack([pairs[i][1] for i in idx]), sr=sr,
+                              chunk_items=chunk_items, **(engine_kwargs or {}))
+            items = run_engine_device(eng, grids)
+            dev_w = select_winners_device(eng, items) if select else None
+        return eng, items, dev_w, stream
+
+    def collect(job):
+        eng, items, dev_w, stream = job
+        with on(stream):
+            w = {name: eng.winners_to_host(v).copy() for name, v in dev_w.items()} if select else None
+            sc = ({name: eng.table_to_host(eng.be.view_bytes_as(buf, np.uint8), pl, eng.U).copy() for name, _, buf, pl in items}
+                  if tables else None)
+        return {"winners": w, "scores": sc, "points": {name: pts for name, pts, _, _ in items},
+                "nominal": sum(pl["n_points"] for _, _, _, pl in items) * eng.U,
+                "unique": sum(pl["unique"] for _, _, _, pl in items) * eng.U}
+
+    outs, pending = [], []
+    streams = _bucket_streams(int(in_flight)) if use_streams else [None]
+    for k, idx in enumerate(buckets):
+        if len(pending) >= len(streams):
+            outs.append(collect(pending.pop(0)))
+        pending.append(enqueue(idx, streams[k % len(streams)]))
+    while pending:
+        outs.append(collect(pending.pop(0)))
+
     scores, winners, points, nominal, unique = None, None, None, 0, 0
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        for L, idx in sorted(by_len.items()):
-            out = sweep_dataset(np.stack([pairs[i][0] for i in idx]), np.stack([pairs[i][1] for i in idx]), grids=grids,
-                                sr=sr, select=select, chunk_items=chunk_items, engine_kwargs=engine_kwargs, tables=tables)
-            points = out["points"]
-            if tables:
-                if scores is None:
-                    scores = {name: np.zeros((len(pairs), sc.shape[1]), dtype=sc.dtype) for name, sc in out["scores"].items()}
-                for name, sc in out["scores"].items():
-                    scores[name][idx] = sc
-            if select:
-                if winners is None:
-                    winners = {name: np.zeros((len(pairs), 3), dtype=w.dtype) for name, w in out["winners"].items()}
-                for name, w in out["winners"].items():
-                    winners[name][idx] = w
-            nominal += out["nominal"]
-            unique += out["unique"]
+    for idx, out in zip(buckets, outs):
+        points = out["points"]
+        if tables:
+            if scores is None:
+                scores = {name: np.zeros((len(pairs), sc.shape[1]), dtype=sc.dtype) for name, sc in out["scores"].items()}
+            for name, sc in out["scores"].items():
+                scores[name][idx] = sc
+        if select:
+            if winners is None:
+                winners = {name: np.zeros((len(pairs), 3), dtype=w.dtype) for name, w in out["winners"].items()}
+            for name, w in out["winners"].items():
+                winners[name][idx] = w
+        nominal += out["nominal"]
+        unique += out["unique"]
     return {"scores": scores, "points": points, "nominal": nominal, "unique": unique, "winners": winners,
             "selection": selection_from_winners(points, winners, False) if select else None}
+
+
+_BUCKET_STREAMS = {}
+
+
+def _bucket_streams(n):
+    """The same streams on every call: the caching allocator keeps one pool of blocks per stream, so fresh streams
+    would mean fresh cudaMallocs for every bucket."""
+    import torch
+    pool = _BUCKET_STREAMS.setdefault(torch.cuda.current_device(), [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream())
+    return pool[:n]
+
+
+def _engine_runtime_is_emulated():
+    from . import engine
+    return engine._runtime.get("backend_factory") is not None

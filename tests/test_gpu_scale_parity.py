@@ -13,6 +13,7 @@
 import multiprocessing as mp
 import os
 import zlib
+import warnings
 
 import numpy as np
 import pytest
@@ -299,3 +300,34 @@ def test_run_dataset_on_device_files_and_resume(tmp_path):
     rows2, summary2 = run_dataset(pairs, out_dirs, str(tmp_path / "summary"), algorithms=algorithms, pesq_scorer=_corr_pesq,
                                   pesq_workers=4, verbose=False)
     assert rows2[:12] == saved and len(rows2) == 16 and summary2["omlsa"]["count"] == 4
+
+
+def test_run_dataset_buckets_in_flight(tmp_path):
+    """Ragged corpus, PESQ-free run: eight length buckets enqueued side by side on their own streams give the same
+    rows and the same winner WAVs as one bucket at a time; rows come back in input order."""
+    from classical_speech_enhancement_b200.dataset import run_dataset
+    from classical_speech_enhancement_b200.speech_enhancement_comparison import algorithms_table
+    shape = {"n_fft": [512, 1024], "hop_length": [128, 256], "noise_percentile": [10.0], "noise_method": ["percentile", "min_tracking"]}
+    small = {"spectralSubtractor": dict({"alpha": [1.0, 3.0], "beta": [0.01, 0.1]}, **shape),
+             "mmse": dict({"alpha": [0.98], "ksi_min": [0.001, 0.1], "gain_min": [0.05], "gain_max": [1.0]}, **shape),
+             "wiener": dict({"alpha": [0.9, 0.98], "gain_floor": [0.02]}, **shape),
+             "omlsa": dict({"alpha": [0.9], "ksi_min": [0.01], "gain_floor": [0.1], "noise_mu": [0.92, 0.98], "q": [0.3, 0.5]}, **shape)}
+    algorithms = [(name, fn, small[name]) for name, fn, _ in algorithms_table()]
+    lengths = [20000, 31000, 20000, 26500, 17001, 40000, 23000, 29000, 33333, 21000, 36000, 18500]
+    pairs = []
+    for u, L in enumerate(lengths):
+        c, n = make_pair(300 + u, L)
+        pairs.append({"stem": f"p{u:03d}_001", "clean": c, "noisy": n, "prepared": True})
+    outs = {}
+    for k in (1, 8):
+        out_dirs = {a[0]: str(tmp_path / f"k{k}" / f"results_{a[0]}") for a in algorithms}
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            rows, _ = run_dataset(pairs, out_dirs, str(tmp_path / f"k{k}" / "summary"), algorithms=algorithms, pesq_scorer=None,
+                                  verbose=False, in_flight=k)
+        assert [r["stem"] for r in rows[::4]] == [p["stem"] for p in pairs] and len(rows) == 4 * len(pairs)
+        outs[k] = (rows, out_dirs)
+    assert outs[1][0] == outs[8][0]
+    for name, d1 in outs[1][1].items():
+        for f in sorted(os.listdir(d1)):
+            assert open(os.path.join(d1, f), "rb").read() == open(os.path.join(outs[8][1][name], f), "rb").read(), f
