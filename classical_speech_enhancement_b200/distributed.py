@@ -2,9 +2,9 @@
 
 Every (utterance, algorithm, grid point) is independent; the only coupling is the
 per-(utterance, algorithm) selection scan, so utterances are partitioned across ranks, each rank
-runs the complete grid for its block with its own caches, and ONE collective at the end gathers
-the per-point score tables for the host-side selection (``torch.distributed`` all_gather: NCCL
-over NVLink on GPUs, gloo in the CPU tests).  The reference has no distributed code at all
+runs the complete grid AND the selection scan for its block with its own caches, and ONE collective
+at the end gathers the winners' records - on request also the per-point score tables
+(``torch.distributed`` all_gather: NCCL over NVLink on GPUs, gloo in the CPU tests).  The reference has no distributed code at all
 (SURVEY.md section 5); this is its B200-native replacement for running ``main()`` for a day.
 """
 import numpy as np
@@ -158,3 +158,55 @@ def sweep_sharded(clean, noisy, grids=None, select=True, chunk_items=DEFAULT_CHU
         selection = sw.selection_from_winners(points, winners, pesq is not None)
     scores = gather_device_scores(eng, items, n_utts, device=device) if tables else None
     return {"scores": scores, "points": points, "winners": winners, "selection": selection, "local_engine": eng}
+
+
+def deal_by_length(lengths, world_size):
+    """Variable-length corpus -> per-rank lists of pair indices: longest first, dealt round-robin, so that every
+    rank holds the same number of pairs (+-1) and nearly the same number of samples."""
+    order = sorted(range(len(lengths)), key=lambda i: (-int(lengths[i]), i))
+    return [order[r::world_size] for r in range(world_size)]
+
+
+def sweep_pairs_sharded(pairs, grids=None, chunk_items=DEFAULT_CHUNK_ITEMS, engine_kwargs=None, in_flight=8):
+    """Variable-length form of :func:`sweep_sharded`: ``pairs`` = the whole corpus as [(clean, noisy)] 1-D arrays on
+    every rank; each rank takes its deal of :func:`deal_by_length`, runs :func:`sweep.sweep_pairs` (one engine per
+    distinct length, several in flight) with the selection on its device, and one all_gather of the 48-byte winner
+    records gives every rank the winners of every pair, in input order."""
+    import torch
+    import torch.distributed as dist
+    from . import sweep as sw
+    grids = grids or sw.DEFAULT_GRIDS
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    deals = deal_by_length([len(p[0]) for p in pairs], world)
+    mine = deals[rank]
+    out = sw.sweep_pairs([pairs[i] for i in mine], grids=grids, select=True, chunk_items=chunk_items,
+                         engine_kwargs=engine_kwargs, tables=False, in_flight=in_flight) if mine else None
+    names = [name for name, _ in grids]
+    points = {name: sw.cached_points(name, ranges) for name, ranges in grids}
+    from ._lib import WINNER_DTYPE as wdt
+    rec = 3 * wdt.itemsize
+    n_pad = max(len(d) for d in deals)
+    host = np.zeros((len(names), n_pad * rec), dtype=np.uint8)
+    for k, name in enumerate(names):
+        if mine:
+            host[k, :len(mine) * rec] = np.ascontiguousarray(out["winners"][name]).reshape(-1).view(np.uint8)
+    if world > 1:
+        send = torch.from_numpy(host)
+        on_gpu = dist.get_backend() == "nccl"
+        if on_gpu:
+            send = send.cuda()
+        recv = torch.empty((world,) + tuple(send.shape), dtype=torch.uint8, device=send.device)
+        if on_gpu:
+            dist.all_gather_into_tensor(recv, send)
+        else:
+            dist.all_gather(list(recv.unbind(0)), send)
+        gathered = recv.cpu().numpy()
+    else:
+        gathered = host[None]
+    winners = {name: np.zeros((len(pairs), 3), dtype=wdt) for name in names}
+    for r, d in enumerate(deals):
+        for k, name in enumerate(names):
+            winners[name][d] = gathered[r, k, :len(d) * rec].view(wdt).reshape(-1, 3)
+    return {"points": points, "winners": winners, "selection": sw.selection_from_winners(points, winners, False),
+            "local_pairs": mine, "nominal": sum(len(points[n]) for n in names) * len(pairs)}

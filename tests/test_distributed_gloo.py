@@ -18,6 +18,17 @@ def test_shard_bounds():
     assert shard_bounds(3, 4) == [0, 1, 2, 3, 3]
 
 
+def _ragged_pairs():
+    from classical_speech_enhancement_b200.synth import make_pair
+    return [make_pair(40 + i, L) for i, L in enumerate((7000, 9001, 6000))]
+
+
+def test_deal_by_length():
+    from classical_speech_enhancement_b200.distributed import deal_by_length
+    assert deal_by_length([5, 9, 7, 9, 1], 2) == [[1, 2, 4], [3, 0]]
+    assert deal_by_length([3], 2) == [[0], []]
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     import torch.distributed as dist
@@ -36,9 +47,13 @@ def _worker(rank, world, port, q):
     rng = np.random.default_rng(3)
     pesq = {"wiener": np.round(rng.uniform(1, 3, (3, 4)), 2)}                 # host-side PESQ table of the whole dataset
     withp = sweep_sharded(clean, noisy, grids=GRID, select=True, pesq=pesq)
+    from classical_speech_enhancement_b200.distributed import sweep_pairs_sharded
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ragged = sweep_pairs_sharded(_ragged_pairs(), grids=GRID)
     if rank == 0:
         q.put((out["scores"]["wiener"], out["winners"]["wiener"], withp["winners"]["wiener"],
-               [b["stoi"]["index"] for b in out["selection"]["wiener"]]))
+               [b["stoi"]["index"] for b in out["selection"]["wiener"]], ragged["winners"]["wiener"]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -57,7 +72,7 @@ def test_two_rank_gloo_equals_single_process():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    scores, winners, winners_pesq, sel = q.get(timeout=240)
+    scores, winners, winners_pesq, sel, ragged = q.get(timeout=300)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -73,6 +88,10 @@ def test_two_rank_gloo_equals_single_process():
         rng = np.random.default_rng(3)
         pesq = {"wiener": np.round(rng.uniform(1, 3, (3, 4)), 2)}
         single_p = sweep_dataset(clean, noisy, grids=GRID, pesq=pesq)
+        from classical_speech_enhancement_b200.sweep import sweep_pairs
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ragged_single = sweep_pairs(_ragged_pairs(), grids=GRID, tables=False)
         host_p = select_all(single_p["scores"], single_p["points"], pesq=pesq)
     finally:
         use_product_runtime()
@@ -87,3 +106,5 @@ def test_two_rank_gloo_equals_single_process():
             a, b = single_p["selection"]["wiener"][u][c], host_p["wiener"][u][c]
             assert a["index"] == b["index"] and a["score"] == b["score"] and a["params"] == b["params"]
     assert single["nominal"] == 3 * 4 and single["unique"] == 3 * 4
+    # variable-length corpus dealt over the two ranks == one process, in input order
+    assert np.array_equal(ragged, ragged_single["winners"]["wiener"]) and ragged["index"][:, 0].min() >= 0
