@@ -87,7 +87,8 @@ def _prepare(pair, target_sr):
 
 
 def run_dataset(pairs, out_dirs, summary_dir, *, algorithms=None, resume=False, start_from="", pesq_scorer="auto",
-                pesq_workers=None, target_sr=16000, write_wavs=True, verbose=True, in_flight=8, checkpoint_seconds=2.0):
+                pesq_workers=None, target_sr=16000, write_wavs=True, verbose=True, in_flight=8, checkpoint_seconds=2.0,
+                prep_workers=None):
     """The reference's batch run over ``pairs`` ([{"stem", "clean", "noisy"}], paths or arrays; arrays already at
     16 kHz and pair-aligned may carry ``"prepared": True``).
 
@@ -96,7 +97,8 @@ def run_dataset(pairs, out_dirs, summary_dir, *, algorithms=None, resume=False, 
     skipped, ``:451-453``), ``summary_means.json`` and ``all_results.csv``.  ``resume=True`` additionally skips
     stems whose winner WAVs exist (``--resume``), ``start_from`` skips everything before that stem (``--start-from``).
     ``in_flight``: length buckets enqueued side by side (PESQ-free runs); ``checkpoint_seconds``: how often at most
-    ``all_results.json`` is rewritten while running.
+    ``all_results.json`` is rewritten while running; ``prep_workers``: host threads of the front end (read, resample,
+    align).
     Returns (all_results, summary)."""
     from .speech_enhancement_comparison import algorithms_table, write_wav_pcm16
     algorithms = algorithms or algorithms_table()
@@ -128,7 +130,16 @@ def run_dataset(pairs, out_dirs, summary_dir, *, algorithms=None, resume=False, 
             scorer = None
 
     todo = [p for p in pairs if any((p["stem"], a[0]) not in have for a in algorithms)]
-    prepared = {p["stem"]: _prepare(p, target_sr) for p in todo}
+    # front end on the host (north_star): WAV read, mono fold, resampling, pair alignment - numpy / scipy / pocketfft
+    # release the GIL, so a thread pool spreads the pairs over the host cores
+    if prep_workers is None:
+        prep_workers = max(1, min(8, (os.cpu_count() or 2) // 2))
+    if prep_workers > 1 and len(todo) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(prep_workers) as ex:
+            prepared = dict(zip((p["stem"] for p in todo), ex.map(lambda p: _prepare(p, target_sr), todo)))
+    else:
+        prepared = {p["stem"]: _prepare(p, target_sr) for p in todo}
     buckets = {}
     for p in todo:
         buckets.setdefault(len(prepared[p["stem"]][0]), []).append(p["stem"])

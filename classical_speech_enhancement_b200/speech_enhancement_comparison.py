@@ -97,7 +97,14 @@ def resample_to(x, sr_in, sr_out):
     g = gcd(int(sr_in), int(sr_out))
     up, down = int(sr_out) // g, int(sr_in) // g
     x = np.asarray(x)
-    y = resample_poly(x.astype(np.float64), up, down, axis=-1, window=_soxr_hq_like_fir(up, down, int(sr_in)))
+    h = _soxr_hq_like_fir(up, down, int(sr_in))
+    if up == 1 and x.ndim == 1 and len(x) >= len(h):
+        # pure decimation (48 -> 16 kHz, the reference's corpus): the same sums as resample_poly - output m is
+        # (x * h)[m * down + (len(h) - 1) / 2] - by overlap-add FFT convolution, 4 x faster for the 637-tap filter
+        from scipy.signal import oaconvolve
+        y = oaconvolve(x.astype(np.float64), h)[(len(h) - 1) // 2::down][:-(-len(x) // down)]
+    else:
+        y = resample_poly(x.astype(np.float64), up, down, axis=-1, window=h)
     return y.astype(np.float32) if x.dtype == np.float32 else y
 
 

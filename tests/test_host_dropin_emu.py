@@ -282,3 +282,35 @@ def test_run_dataset_rows_wavs_and_resume(tmp_path):
                                algorithms=algorithms[1:], pesq_scorer=None and "auto" or "auto", verbose=False)
     assert rows3[0]["pesq_noisy"] is None and rows3[0]["stoi_pesqopt"] is None and rows3[0]["stoi_stoiopt"] is not None
     assert sorted(os.listdir(tmp_path / "nopesq" / "wiener")) == [f"{pairs[0]['stem']}_wiener_optimized_stoi.wav"]
+
+
+def test_front_end_resampler_and_threaded_prepare():
+    """``resample_to`` (``speech_enhancement_comparison.py:23-27``): the 48 -> 16 kHz decimation by overlap-add FFT
+    convolution gives the polyphase sums of ``resample_poly`` with the same filter and equals the test-side
+    resampler the oracle was pinned with; dtype, length and short-input behaviour as ``librosa.resample``; the
+    dataset run's threaded front end returns what the serial one does."""
+    from scipy.signal import resample_poly
+    from classical_speech_enhancement_b200 import speech_enhancement_comparison as sec
+    from classical_speech_enhancement_b200.dataset import _prepare
+    from tests.golden_util import soxr_hq_like_48k_to_16k
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "p257_135_48k.npz"))
+    x = d["clean"].astype(np.float64) / 32768.0
+    h = sec._soxr_hq_like_fir(1, 3, 48000)
+    y = sec.resample_to(x, 48000, 16000)
+    assert y.dtype == np.float64 and len(y) == -(-len(x) // 3)
+    assert np.abs(y - resample_poly(x, 1, 3, window=h)).max() < 1e-14
+    assert np.abs(y - soxr_hq_like_48k_to_16k(x)).max() < 6e-8       # that one rounds to float32 as librosa does
+    assert sec.resample_to(x.astype(np.float32), 48000, 16000).dtype == np.float32
+    short = x[:100]                                              # shorter than the filter: the polyphase path
+    assert np.array_equal(sec.resample_to(short, 48000, 16000), resample_poly(short, 1, 3, window=h))
+    assert sec.resample_to(x, 16000, 16000) is x
+    up = sec.resample_to(x[:4000], 16000, 48000)                 # interpolation keeps the polyphase path
+    assert len(up) == 12000
+    pairs = [{"stem": f"s{i}", "clean": d["clean"][i * 1000:].astype(np.float32) / 32768, "noisy": d["noisy"][i * 1000:].astype(np.float32) / 32768,
+              "sr": 48000} for i in range(4)]
+    from concurrent.futures import ThreadPoolExecutor
+    serial = [_prepare(p, 16000) for p in pairs]
+    with ThreadPoolExecutor(4) as ex:
+        threaded = list(ex.map(lambda p: _prepare(p, 16000), pairs))
+    for a, b in zip(serial, threaded):
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
