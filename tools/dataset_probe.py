@@ -1,5 +1,6 @@
 """Dataset-level run over a ragged synthetic corpus (no PESQ): seconds per pair with one bucket at a time and with
-several in flight: python tools/dataset_probe.py [--pairs 48]"""
+several in flight: python tools/dataset_probe.py [--pairs 48] [--files]
+(--files: the corpus as 48 kHz PCM16 WAV files on disk, so that read + resample + pair alignment are inside the time)"""
 import os
 import sys
 import tempfile
@@ -20,6 +21,16 @@ pairs = []
 for i, L in enumerate(int(v) for v in rng.integers(32000, 64000, n)):
     c, x = make_pair(i, L)
     pairs.append({"stem": f"p{i:03d}_001", "clean": c, "noisy": x, "prepared": True})
+files = "--files" in sys.argv
+corpus = tempfile.TemporaryDirectory()
+if files:
+    from classical_speech_enhancement_b200.dataset import find_pairs
+    from classical_speech_enhancement_b200.speech_enhancement_comparison import write_wav_pcm16
+    for i, L in enumerate(int(v) for v in rng.integers(3 * 32000, 3 * 64000, n)):
+        c, x = make_pair(i, L)
+        write_wav_pcm16(os.path.join(corpus.name, f"p{i:03d}_001_clean.wav"), c, 48000)
+        write_wav_pcm16(os.path.join(corpus.name, f"p{i:03d}_001_noisy.wav"), x, 48000)
+    pairs = sorted(find_pairs(corpus.name), key=lambda p: p["stem"])
 for k in (8, 1, 8):                                             # first pass warms allocator pools and plans
     with tempfile.TemporaryDirectory() as d:
         out_dirs = {a: os.path.join(d, f"results_{a}") for a in ("spectralSubtractor", "mmse", "wiener", "omlsa")}
