@@ -106,6 +106,7 @@ class CseLibrary:
             raise AttributeError(name)
         fn = getattr(self._dll, sym)
         if SIGNATURES[sym][0] is not _i or name in ("abi_version", "dtype", "bins_padded", "num_frames", "max_score_length"):
+            self.__dict__[name] = fn                 # next lookup is a plain attribute, not __getattr__
             return fn
 
         def call(*args):
@@ -113,6 +114,7 @@ class CseLibrary:
             if rc != CSE_OK:
                 raise CseError(rc, self.last_error())
             return rc
+        self.__dict__[name] = call
         return call
 
 

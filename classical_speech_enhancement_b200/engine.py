@@ -88,6 +88,9 @@ class TorchCudaBackend:
             raise _lib.CseLibraryError("no CUDA device: this path has no CPU fallback")
         self.torch = torch
         self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self._dev_index = self.device.index
+        self._current_stream_id = torch._C._cuda_getCurrentStream
+        self._stream_handles = {}
 
     def empty(self, shape, dtype):
         t = self.torch
@@ -113,7 +116,13 @@ class TorchCudaBackend:
         return ctypes.c_void_p(buf.data_ptr() + int(byte_offset))
 
     def stream(self):
-        return ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+        """Raw handle of torch's current stream on this device (one call per launch: the stream object and its
+        ``c_void_p`` are cached per stream id instead of being rebuilt by ``torch.cuda.current_stream``)."""
+        sid = self._current_stream_id(self._dev_index)[0]
+        h = self._stream_handles.get(sid)
+        if h is None:
+            h = self._stream_handles[sid] = ctypes.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+        return h
 
     def synchronize(self):
         self.torch.cuda.current_stream(self.device).synchronize()
@@ -184,6 +193,15 @@ class TorchCudaBackend:
         self.torch.cuda.current_stream(self.device).wait_event(handle[1])
 
 
+def _synchronize_all(be):
+    """Whole-device synchronisation (every stream), where the backend has one."""
+    t = getattr(be, "torch", None)
+    if t is not None:
+        t.cuda.synchronize(be.device)
+    else:
+        be.synchronize()
+
+
 class SweepEngine:
     """One batch of ``U`` equal-length (clean, noisy) pairs resident on one device."""
 
@@ -216,6 +234,7 @@ class SweepEngine:
         self.clean = be.from_host(self.clean_host)
         self.noisy = be.from_host(np.ascontiguousarray(noisy, dtype=self.real))
         self.h2d_bytes = 2 * clean.size * np.dtype(self.real).itemsize
+        self._nf = {}
         self._stft = {}
         self._pow = {}
         self._noise = {}
@@ -279,7 +298,10 @@ class SweepEngine:
         return self._ws[name][0]
 
     def n_frames(self, n_fft, hop):
-        return self.lib.num_frames(self.L, hop)
+        nf = self._nf.get(hop)
+        if nf is None:
+            nf = self._nf[hop] = self.lib.num_frames(self.L, hop)
+        return nf
 
     def stft(self, n_fft, hop):
         """Y [U][nf][nbp] (complex as interleaved reals) of the noisy signals, cached per shape."""
@@ -390,12 +412,45 @@ class SweepEngine:
                              "col0": col, "member_idx": member_idx, "row_idx": row_idx, "members": g["members"]})
                 col += n_rows
             out = {"groups": info, "unique": col, "n_points": len(points), "gamma": split_mu}
+            out["shared"] = out                       # the cached object itself: carries the per-device constants
             _PLAN_CACHE[key] = out
             while len(_PLAN_CACHE) > _PLAN_CACHE_MAX:
-                _PLAN_CACHE.popitem(last=False)
+                _, old = _PLAN_CACHE.popitem(last=False)
+                if old.get("dev"):
+                    _synchronize_all(self.be)          # its device constants may still be read by enqueued kernels
         pl = dict(out)
         self._plans[key] = pl
         return pl
+
+    def _plan_constants(self, pl):
+        """Device-side constants of a plan - the packed parameter rows of every group and the nominal-table maps of
+        ``cse_expand_scores`` for this batch size - uploaded ONCE per (plan, device) and shared by every engine and
+        stream of the process (a corpus of one-pair buckets would otherwise re-upload ~70 small arrays per pair).
+        The first upload is followed by a synchronisation, so that streams other than the uploading one may use
+        the buffers without an event."""
+        shared = pl["shared"]
+        dkey = getattr(self.be, "device", "host").__str__()
+        dev = shared.setdefault("dev", {}).get(dkey)
+        fresh = False
+        if dev is None:
+            dev = shared["dev"][dkey] = {"params": [self.be.from_host(g["params_host"]) for g in pl["groups"]], "maps": OrderedDict()}
+            fresh = True
+        if self.U not in dev["maps"]:
+            base = np.zeros(pl["n_points"], dtype=np.int32)
+            stride = np.zeros(pl["n_points"], dtype=np.int32)
+            for g in pl["groups"]:
+                base[g["member_idx"]] = self.U * g["col0"] + g["row_idx"]
+                stride[g["member_idx"]] = g["n_rows"]
+            dev["maps"][self.U] = (self.be.from_host(base), self.be.from_host(stride))
+            fresh = True
+            while len(dev["maps"]) > 8:
+                _synchronize_all(self.be)              # a kernel of another stream may still read the evicted maps
+                dev["maps"].popitem(last=False)
+        else:
+            dev["maps"].move_to_end(self.U)
+        if fresh:
+            self.be.synchronize()
+        return dev
 
     def _validate_shapes(self, points):
         """The build's operating range (include/cse.h), checked once per grid with a message that names the
@@ -430,8 +485,9 @@ class SweepEngine:
         be, lib_ = self.be, self.lib
         rec = self.lib.score_dtype.itemsize
         uniq = be.empty((max(1, self.U * pl["unique"] * rec),), np.uint8)
-        keep = []
-        for g in pl["groups"]:
+        dev = self._plan_constants(pl)
+        keep = [dev]
+        for gi, g in enumerate(pl["groups"]):
             key = g["key"]
             n_fft, hop = key[0], key[1]
             Y = self.stft(n_fft, hop)
@@ -440,11 +496,7 @@ class SweepEngine:
             else:
                 N, tv = self.noise(key)
             n_rows = g["n_rows"]
-            pcache = pl.setdefault("params_dev", {})          # per engine: one upload per group, reused by later sweeps
-            params = pcache.get(id(g))
-            if params is None:
-                params = pcache[id(g)] = be.from_host(g["params_host"])
-            keep.append(params)
+            params = dev["params"][gi]
             sc_ptr = be.ptr_at(uniq, self.U * g["col0"] * rec)          # group block [U][n_rows]
             total = self.U * n_rows
             rb = np.dtype(self.real).itemsize
@@ -487,14 +539,7 @@ class SweepEngine:
             if chunk_sink is not None:
                 self._export_retire(chunk_sink, keep=0)
         table = (be.zeros if u_pad > self.U else be.empty)((u_pad * pl["n_points"] * rec,), np.uint8)
-        if "dev_maps" not in pl or pl["dev_maps"][0] != self.U:
-            base = np.zeros(pl["n_points"], dtype=np.int32)
-            stride = np.zeros(pl["n_points"], dtype=np.int32)
-            for g in pl["groups"]:
-                base[g["member_idx"]] = self.U * g["col0"] + g["row_idx"]
-                stride[g["member_idx"]] = g["n_rows"]
-            pl["dev_maps"] = (self.U, be.from_host(base), be.from_host(stride))
-        _, dbase, dstride = pl["dev_maps"]
+        dbase, dstride = dev["maps"][self.U]
         lib_.expand_scores(be.ptr(uniq), be.ptr(dbase), be.ptr(dstride), self.U, pl["n_points"], be.ptr(table), be.stream())
         self.launches += 1
         self._keepalive = (keep, uniq)  # must outlive the enqueued kernels
@@ -586,14 +631,15 @@ class SweepEngine:
         percent of the sweep that found them."""
         alg = ALGORITHM_IDS[alg_name] if isinstance(alg_name, str) else int(alg_name)
         pl = self._plan(alg, points)
-        if "point_loc" not in pl:
+        if "point_loc" not in pl["shared"]:
             grp = np.zeros(pl["n_points"], dtype=np.int32)
             row = np.zeros(pl["n_points"], dtype=np.int32)
             for gi, g in enumerate(pl["groups"]):
                 grp[g["member_idx"]] = gi
                 row[g["member_idx"]] = g["row_idx"]
-            pl["point_loc"] = (grp, row)
-        grp, row = pl["point_loc"]
+            pl["shared"]["point_loc"] = (grp, row)
+        grp, row = pl["shared"]["point_loc"]
+        dev = self._plan_constants(pl)
         be, lib_ = self.be, self.lib
         by_group = {}
         for u, i in wanted:
@@ -610,7 +656,7 @@ class SweepEngine:
                 N, tv = self.noise(key)
             uniq = sorted({(u, int(row[i])) for u, i in lst})                 # identical device candidates once
             items = np.array([u * g["n_rows"] + r for u, r in uniq], dtype=np.int32)
-            params = be.from_host(g["params_host"])
+            params = dev["params"][gi]
             dev_items = be.from_host(items)
             wav = be.empty((len(items), self.L), self.real)
             lib_.enhance_list(be.ptr(self.tables), alg, be.ptr(Y), be.ptr(N), int(tv), self.L, n_fft, hop, be.ptr(params),

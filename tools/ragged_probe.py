@@ -47,4 +47,4 @@ if "--profile" in sys.argv:
     pr.enable()
     sweep_pairs(ragged, tables=False)
     pr.disable()
-    pstats.Stats(pr).sort_stats("tottime").print_stats(18)
+    pstats.Stats(pr).sort_stats("tottime").print_stats(45)
