@@ -87,7 +87,7 @@ def _prepare(pair, target_sr):
 
 
 def run_dataset(pairs, out_dirs, summary_dir, *, algorithms=None, resume=False, start_from="", pesq_scorer="auto",
-                pesq_workers=None, target_sr=16000, write_wavs=True, verbose=True, in_flight=8, checkpoint_seconds=2.0,
+                pesq_workers=None, target_sr=16000, write_wavs=True, verbose=True, in_flight=12, checkpoint_seconds=2.0,
                 prep_workers=None):
     """The reference's batch run over ``pairs`` ([{"stem", "clean", "noisy"}], paths or arrays; arrays already at
     16 kHz and pair-aligned may carry ``"prepared": True``).
@@ -163,7 +163,8 @@ def run_dataset(pairs, out_dirs, summary_dir, *, algorithms=None, resume=False, 
             clean = np.stack([prepared[s][0] for s in stems])
             noisy = np.stack([prepared[s][1] for s in stems])
             chunk = PESQ_CHUNK_ITEMS if scorer is not None else None
-            eng = SweepEngine(clean, noisy, sr=target_sr, **({"chunk_items": chunk} if chunk else {}))
+            eng = SweepEngine(clean, noisy, sr=target_sr, **({"chunk_items": chunk} if chunk else {}),
+                              **({"side_streams": 0} if stream is not None else {}))
             base = eng.baseline_device()
             base_pesq = [None] * len(stems)
             if scorer is not None:

@@ -167,7 +167,7 @@ def deal_by_length(lengths, world_size):
     return [order[r::world_size] for r in range(world_size)]
 
 
-def sweep_pairs_sharded(pairs, grids=None, chunk_items=DEFAULT_CHUNK_ITEMS, engine_kwargs=None, in_flight=8):
+def sweep_pairs_sharded(pairs, grids=None, chunk_items=DEFAULT_CHUNK_ITEMS, engine_kwargs=None, in_flight=12):
     """Variable-length form of :func:`sweep_sharded`: ``pairs`` = the whole corpus as [(clean, noisy)] 1-D arrays on
     every rank; each rank takes its deal of :func:`deal_by_length`, runs :func:`sweep.sweep_pairs` (one engine per
     distinct length, several in flight) with the selection on its device, and one all_gather of the 48-byte winner

@@ -32,10 +32,15 @@ MAX_WAV_WORKSPACE_BYTES = 8 << 30
 #: thread-emulated build to exercise the host logic without a GPU.
 _runtime = {"lib": None, "backend_factory": None, "reuse_result_buffers": False,
             # share the candidate-invariant front of the Wiener / MMSE / Log-MMSE gain rules (cse_gamma) across a group
-            "gamma": os.environ.get("CSE_GAMMA", "1") != "0"}
+            "gamma": os.environ.get("CSE_GAMMA", "1") != "0",
+            # a single pair: all groups of a grid scored by one align + one STOI launch (sweep_device)
+            "fuse_single": os.environ.get("CSE_FUSE_SINGLE", "1") != "0",
+            # ... and its groups' enhance launches spread over this many side streams (0: all on the current stream)
+            "fuse_streams": int(os.environ.get("CSE_FUSE_STREAMS", "4"))}
 _PLAN_CACHE = OrderedDict()      # (algorithm, grid digest, frame-count signature) -> host-side launch plan, LRU
 _PLAN_CACHE_MAX = 32
 _PINNED_POOL = {}
+_SIDE_STREAMS = {}              # (device index, id of the stream they fork from) -> [(torch stream, raw handle)]
 _TABLES_CACHE = {}               # (library, device) -> constant tables buffer (twiddles, windows, resampler taps)
 
 
@@ -127,6 +132,32 @@ class TorchCudaBackend:
     def synchronize(self):
         self.torch.cuda.current_stream(self.device).synchronize()
 
+    # --- fork / join over side streams: independent small launches of ONE engine side by side
+    def side_streams(self, n):
+        """``n`` side streams belonging to the CURRENT stream of this device (process-wide, persistent: engines that
+        work on the same stream share them, engines on different streams - the buckets a corpus driver keeps in
+        flight - never do, or their forks and joins would chain them to each other) -> (stream objects, handles)."""
+        pool = _SIDE_STREAMS.setdefault((self._dev_index, self._current_stream_id(self._dev_index)[0]), [])
+        while len(pool) < n:
+            st = self.torch.cuda.Stream(device=self.device)
+            pool.append((st, ctypes.c_void_p(st.cuda_stream)))
+        return [p[0] for p in pool[:n]], [p[1] for p in pool[:n]]
+
+    def fork(self, streams):
+        """The side streams wait for everything enqueued so far on the current stream."""
+        ev = self.torch.cuda.Event()
+        ev.record(self.torch.cuda.current_stream(self.device))
+        for st in streams:
+            st.wait_event(ev)
+
+    def join(self, streams):
+        """The current stream waits for everything enqueued so far on the side streams."""
+        cur = self.torch.cuda.current_stream(self.device)
+        for st in streams:
+            ev = self.torch.cuda.Event()
+            ev.record(st)
+            cur.wait_event(ev)
+
     def event(self):
         e = self.torch.cuda.Event(enable_timing=True)
         e.record(self.torch.cuda.current_stream(self.device))
@@ -205,7 +236,8 @@ def _synchronize_all(be):
 class SweepEngine:
     """One batch of ``U`` equal-length (clean, noisy) pairs resident on one device."""
 
-    def __init__(self, clean, noisy, sr=SR, lib=None, backend=None, chunk_items=DEFAULT_CHUNK_ITEMS, prepare_scoring=True):
+    def __init__(self, clean, noisy, sr=SR, lib=None, backend=None, chunk_items=DEFAULT_CHUNK_ITEMS, prepare_scoring=True,
+                 side_streams=None):
         if sr != SR:
             raise ValueError("the sweep runs at 16 kHz (the reference resamples every pair to 16 kHz first)")
         self.lib = lib if lib is not None else (_runtime["lib"] or _lib.load())
@@ -218,6 +250,9 @@ class SweepEngine:
         if clean.shape != noisy.shape or clean.ndim != 2:
             raise ValueError("clean and noisy must both be [U, L]")
         self.U, self.L = clean.shape
+        # one-pair engines spread their groups' launches over side streams (sweep_device) - unless a corpus driver
+        # already keeps several engines in flight on streams of their own (measured: the two do not add up)
+        self.side_streams = int(_runtime.get("fuse_streams") or 0) if side_streams is None else int(side_streams)
         if self.has_clean and prepare_scoring and self.L > self.lib.max_score_length(sr):
             raise _lib.CseError(_lib.CSE_EUNSUPPORTED, f"utterances of {self.L} samples exceed the scoring kernels' limit of "
                                 f"{self.lib.max_score_length(sr)} samples (about 38 s at 16 kHz); split the recording")
@@ -276,6 +311,9 @@ class SweepEngine:
         if getattr(self, "_timing", None) is None or not hasattr(self.be, "event"):
             return None
         return self.be.event()
+
+    def _timing_off(self):
+        return getattr(self, "_timing", None) is None
 
     def _record(self, tag, n_items, e0, e1):
         if e0 is not None:
@@ -487,7 +525,36 @@ class SweepEngine:
         uniq = be.empty((max(1, self.U * pl["unique"] * rec),), np.uint8)
         dev = self._plan_constants(pl)
         keep = [dev]
-        for gi, g in enumerate(pl["groups"]):
+        rb = np.dtype(self.real).itemsize
+        # One pair (the reference's own call pattern: optimize_parameters per pair and algorithm, and every bucket of
+        # a variable-length corpus): a group is a few dozen to a few hundred candidates, far below one wave of the
+        # score kernels.  With U == 1 the groups' score blocks are consecutive in the unique table, so every group
+        # enhances into its slice of ONE waveform buffer and the whole grid is aligned and scored by one launch each.
+        fused = (self.U == 1 and chunk_sink is None and _runtime.get("fuse_single", True) and 0 < pl["unique"] <= self.chunk_items
+                 and pl["unique"] * self.L * rb <= MAX_WAV_WORKSPACE_BYTES)
+        if fused:
+            wav_all = self._workspace("wav", pl["unique"] * self.L * rb)
+            t_first = self._tick()
+            # the groups are independent and write disjoint slices: their (small) launches go round-robin onto side
+            # streams - forked after the spectrograms / noise PSDs they read are enqueued, joined before the scoring
+            inputs = []
+            for g in pl["groups"]:
+                Y = self.stft(g["key"][0], g["key"][1])
+                inputs.append((Y,) + ((self.gamma(g["key"]), 2) if pl.get("gamma") else self.noise(g["key"])))
+            n_side = self.side_streams if hasattr(be, "side_streams") and self._timing_off() else 0
+            side, handles = be.side_streams(n_side) if n_side > 1 else ([], [be.stream()])
+            if side:
+                be.fork(side)
+            p_tab = be.ptr(self.tables)
+            for gi, g in enumerate(pl["groups"]):
+                Y, N, tv = inputs[gi]
+                lib_.enhance_items(p_tab, alg, be.ptr(Y), be.ptr(N), int(tv), self.L, g["key"][0], g["key"][1],
+                                   be.ptr(dev["params"][gi]), g["n_rows"], 0, g["n_rows"],
+                                   be.ptr_at(wav_all, g["col0"] * self.L * rb), handles[gi % len(handles)])
+            self.launches += len(pl["groups"])
+            if side:
+                be.join(side)
+        for gi, g in enumerate(() if fused else pl["groups"]):
             key = g["key"]
             n_fft, hop = key[0], key[1]
             Y = self.stft(n_fft, hop)
@@ -499,7 +566,6 @@ class SweepEngine:
             params = dev["params"][gi]
             sc_ptr = be.ptr_at(uniq, self.U * g["col0"] * rec)          # group block [U][n_rows]
             total = self.U * n_rows
-            rb = np.dtype(self.real).itemsize
             # near-equal chunks, as many as the total rounds to: a group of 1.04 chunks runs as ONE launch (a few
             # hundred candidates launched on their own would cost two waves of the whole GPU), never more than 1.5 chunks
             n_chunks = max(1, int(total / self.chunk_items + 0.5))
@@ -538,6 +604,21 @@ class SweepEngine:
                     self._exports.append((handle, g, i0, n))
             if chunk_sink is not None:
                 self._export_retire(chunk_sink, keep=0)
+        if fused:
+            n = pl["unique"]
+            nbytes = lib_.score_workspace_bytes(n, self.L, SR)
+            ws = self._workspace("score", nbytes)
+            t1 = self._tick()
+            sargs = (be.ptr(self.tables), be.ptr(wav_all), 0, n, n, self.L, SR, be.ptr(self.clean), be.ptr(self.cache), 1,
+                     be.ptr(uniq), be.ptr(ws), nbytes, be.stream())
+            lib_.align_items(*sargs)
+            t2 = self._tick()
+            lib_.stoi_items(*sargs)
+            t3 = self._tick()
+            self._record(("enhance", alg, 0, 0, "one pair"), n, t_first, t1)
+            self._record(("align", alg, 0, 0, "one pair"), n, t1, t2)
+            self._record(("stoi", alg, 0, 0, "one pair"), n, t2, t3)
+            self.launches += 2
         table = (be.zeros if u_pad > self.U else be.empty)((u_pad * pl["n_points"] * rec,), np.uint8)
         dbase, dstride = dev["maps"][self.U]
         lib_.expand_scores(be.ptr(uniq), be.ptr(dbase), be.ptr(dstride), self.U, pl["n_points"], be.ptr(table), be.stream())

@@ -180,7 +180,7 @@ def sweep_dataset(clean, noisy, grids=DEFAULT_GRIDS, sr=16000, select=True, chun
 
 
 def sweep_pairs(pairs, grids=DEFAULT_GRIDS, sr=16000, select=True, chunk_items=DEFAULT_CHUNK_ITEMS, engine_kwargs=None,
-                tables=True, in_flight=8):
+                tables=True, in_flight=12):
     """Variable-length form of :func:`sweep_dataset`: ``pairs`` is a list of (clean, noisy) 1-D arrays
     (each pair equal length, pair-aligned, 16 kHz).  Pairs are bucketed by length - one engine (and
     one set of cached spectrograms) per distinct length - and results are returned in input order.
@@ -213,7 +213,7 @@ def sweep_pairs(pairs, grids=DEFAULT_GRIDS, sr=16000, select=True, chunk_items=D
     def enqueue(idx, stream):
         with on(stream):
             eng = SweepEngine(np.stack([pairs[i][0] for i in idx]), np.stack([pairs[i][1] for i in idx]), sr=sr,
-                              chunk_items=chunk_items, **(engine_kwargs or {}))
+                              chunk_items=chunk_items, **dict({"side_streams": 0} if stream is not None else {}, **(engine_kwargs or {})))
             items = run_engine_device(eng, grids)
             dev_w = select_winners_device(eng, items) if select else None
         return eng, items, dev_w, stream

@@ -331,3 +331,26 @@ def test_run_dataset_buckets_in_flight(tmp_path):
     for name, d1 in outs[1][1].items():
         for f in sorted(os.listdir(d1)):
             assert open(os.path.join(d1, f), "rb").read() == open(os.path.join(outs[8][1][name], f), "rb").read(), f
+
+
+def test_single_pair_one_score_launch_equals_per_group_launches():
+    """The reference's call pattern - one pair, one algorithm, the full grid: every group enhanced into its slice
+    of one buffer, ONE align and ONE STOI launch for the whole grid.  Tables bit-identical to per-group launches
+    for all four full grids, and the winners identical."""
+    from classical_speech_enhancement_b200 import engine as eng_mod
+    from classical_speech_enhancement_b200.engine import SweepEngine
+    from classical_speech_enhancement_b200.sweep import DEFAULT_GRIDS, cached_points
+    c, n = make_pair(77, 50000)
+    tabs = {}
+    for fuse in (True, False):
+        eng_mod._runtime["fuse_single"] = fuse
+        try:
+            eng = SweepEngine(c[None], n[None])
+            tabs[fuse] = {name: eng.sweep(name, cached_points(name, ranges)).copy() for name, ranges in DEFAULT_GRIDS}
+            tabs[fuse]["launches"] = eng.launches
+        finally:
+            eng_mod._runtime["fuse_single"] = True
+    for name, _ in DEFAULT_GRIDS:
+        assert tabs[True][name].tobytes() == tabs[False][name].tobytes(), name
+        assert (tabs[True][name]["flags"] & 1).all()
+    assert tabs[True]["launches"] < 0.7 * tabs[False]["launches"]
