@@ -322,9 +322,9 @@ def test_single_pair_scores_all_groups_in_one_launch():
     path) gives the same rows."""
     from classical_speech_enhancement_b200 import engine as eng_mod
     from classical_speech_enhancement_b200.engine import SweepEngine
-    ranges = {"alpha": [0.9, 0.98], "gain_floor": [0.02, 0.1], "n_fft": [256, 512], "hop_length": [128],
+    ranges = {"alpha": [0.9, 0.98], "gain_floor": [0.05], "n_fft": [256], "hop_length": [128],
               "noise_percentile": [10.0], "noise_method": ["percentile", "min_tracking", "true_noise"]}
-    pts = grid.grid_points(ranges)
+    pts = grid.grid_points(ranges)                               # three noise-PSD groups of two candidates
     c0, n0 = make_pair(5, 14000)
     c1, n1 = make_pair(6, 14000)
     one = SweepEngine(c0[None], n0[None])
