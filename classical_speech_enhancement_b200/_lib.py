@@ -45,6 +45,7 @@ SIGNATURES = {
     "cse_sweep_workspace_bytes": (_sz, [_i, _i, _i]),
     "cse_enhance_items": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
     "cse_enhance_list": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
+    "cse_enhance_groups": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
     "cse_score_items": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "cse_align_items": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "cse_stoi_items": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
@@ -58,6 +59,11 @@ SIGNATURES = {
 #: cse_winner_t (include/cse.h)
 WINNER_DTYPE = np.dtype([("index", np.int32), ("lag", np.int32), ("flags", np.int32), ("reserved", np.int32),
                          ("score", np.float64), ("stoi", np.float64), ("pesq", np.float64), ("snr", np.float64)])
+
+
+class EnhanceGroup(ctypes.Structure):
+    """``cse_enhance_group`` (include/cse.h): one noise-PSD group of a grouped enhance launch."""
+    _fields_ = [("Y", _vp), ("N", _vp), ("params", _vp), ("out", _vp), ("hop", _i), ("n_params", _i)]
 
 
 class CseLibraryError(RuntimeError):

@@ -222,4 +222,81 @@ extern "C" int cse_enhance_list(const void* tables, int algorithm, const void* Y
     return enhance_items(tables, algorithm, Y, N, noise_tv, length, n_fft, hop, params, n_params, 0, n_items, out, stream, items);
 }
 
+// ---- grouped launches (several noise-PSD groups of one instantiation)
+template <int ALG, int LOG2N>
+static int launch_enhance_groups(const EnhanceGroupsArgs& ga, int n_blocks, void* stream) {
+    typedef EnhanceCfg<LOG2N> C;
+    constexpr bool STAGED = LOG2N <= CSE_ENH_STAGED_MAX_LOG2N && LOG2N >= CSE_ENH_STAGED_MIN_LOG2N;
+    size_t smem = 0;
+    for (int k = 0; k < ga.n_groups; ++k) {
+        const size_t sk = enhance_smem_bytes<LOG2N>(ga.g[k].hop, ga.noise_tv, STAGED);
+        smem = sk > smem ? sk : smem;
+    }
+    if (ga.noise_tv == 2) {
+        if constexpr (ALG == 0) return fail(CSE_EINVAL, "spectral subtraction takes the noise PSD, not the a-posteriori SNR (noise_tv 2)");
+        else {
+            auto kfn = enhance_groups_kernel<ALG, LOG2N, STAGED, true, true>;
+            CSE_SMEM_OPT_IN(kfn, enhance_smem_bytes<LOG2N>(C::NFFT / 2, 1, STAGED));
+            CSE_LAUNCH(kfn, n_blocks, C::NT, smem, stream, ga);
+        }
+    } else if (ga.noise_tv) {
+        auto kfn = enhance_groups_kernel<ALG, LOG2N, STAGED, true>;
+        CSE_SMEM_OPT_IN(kfn, enhance_smem_bytes<LOG2N>(C::NFFT / 2, 1, STAGED));
+        CSE_LAUNCH(kfn, n_blocks, C::NT, smem, stream, ga);
+    } else {
+        auto kfn = enhance_groups_kernel<ALG, LOG2N, STAGED, false>;
+        CSE_SMEM_OPT_IN(kfn, enhance_smem_bytes<LOG2N>(C::NFFT / 2, 0, STAGED));
+        CSE_LAUNCH(kfn, n_blocks, C::NT, smem, stream, ga);
+    }
+    return check_launch("enhance_groups_kernel");
+}
+template <int ALG>
+static int dispatch_enhance_groups(const EnhanceGroupsArgs& ga, int n_fft, int n_blocks, void* stream) {
+    switch (n_fft) {
+        case 256: return launch_enhance_groups<ALG, 8>(ga, n_blocks, stream);
+        case 512: return launch_enhance_groups<ALG, 9>(ga, n_blocks, stream);
+        case 1024: return launch_enhance_groups<ALG, 10>(ga, n_blocks, stream);
+        default: return launch_enhance_groups<ALG, 11>(ga, n_blocks, stream);
+    }
+}
+
+extern "C" int cse_enhance_groups(const void* tables, int algorithm, int noise_tv, int n_utts, int length, int n_fft,
+                                  const cse_enhance_group* groups, int n_groups, void* stream) {
+    CSE_REQUIRE(tables && groups, "NULL argument");
+    CSE_REQUIRE(valid_nfft(n_fft), "n_fft %d not in {256,512,1024,2048}", n_fft);
+    CSE_REQUIRE(n_utts > 0 && n_groups > 0 && length > n_fft / 2, "bad sizes");
+    CSE_REQUIRE(algorithm >= 0 && algorithm <= 3, "unknown algorithm %d", algorithm);
+    CSE_REQUIRE(noise_tv >= 0 && noise_tv <= 2, "noise_tv %d not in {0,1,2}", noise_tv);
+    for (int k = 0; k < n_groups; ++k) {
+        CSE_REQUIRE(groups[k].Y && groups[k].N && groups[k].params && groups[k].out, "NULL argument in group %d", k);
+        CSE_REQUIRE(groups[k].hop > 0 && groups[k].hop <= n_fft / 2 && groups[k].hop % 2 == 0, "hop %d must be even and <= n_fft/2", groups[k].hop);
+        CSE_REQUIRE(groups[k].n_params > 0, "group %d has no parameter rows", k);
+    }
+    for (int g0 = 0; g0 < n_groups; g0 += CSE_ENH_MAX_GROUPS) {       // as many launches as the descriptor table needs
+        EnhanceGroupsArgs ga;
+        ga.T = (const CseTables*)tables; ga.noise_tv = noise_tv; ga.L = length; ga.eps = alg_eps(algorithm);
+        ga.n_groups = n_groups - g0 < CSE_ENH_MAX_GROUPS ? n_groups - g0 : CSE_ENH_MAX_GROUPS;
+        int blocks = 0;
+        for (int k = 0; k < ga.n_groups; ++k) {
+            const cse_enhance_group& src = groups[g0 + k];
+            EnhanceGroup& g = ga.g[k];
+            g.Y = (const real2*)src.Y; g.N = (const real*)src.N; g.params = src.params; g.out = (real*)src.out;
+            g.hop = src.hop; g.n_frames = cse_num_frames(length, src.hop); g.n_params = src.n_params;
+            g.hop_shift = (src.hop & (src.hop - 1)) == 0 ? cse_ilog2(src.hop) : -1;
+            g.first_block = blocks; g.reserved = 0;
+            blocks += n_utts * src.n_params;
+        }
+        for (int k = ga.n_groups; k < CSE_ENH_MAX_GROUPS; ++k) ga.g[k] = ga.g[0];
+        int rc = CSE_OK;
+        switch (algorithm) {
+            case CSE_ALG_SS: rc = dispatch_enhance_groups<0>(ga, n_fft, blocks, stream); break;
+            case CSE_ALG_WIENER: rc = dispatch_enhance_groups<1>(ga, n_fft, blocks, stream); break;
+            case CSE_ALG_MMSE: rc = dispatch_enhance_groups<2>(ga, n_fft, blocks, stream); break;
+            default: rc = dispatch_enhance_groups<3>(ga, n_fft, blocks, stream); break;
+        }
+        if (rc != CSE_OK) return rc;
+    }
+    return CSE_OK;
+}
+
 #include "cse_lib_noise_score.inl"

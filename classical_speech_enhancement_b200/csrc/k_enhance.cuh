@@ -226,8 +226,12 @@ CSE_D void emit_edge_pair(real2 acc, int p, int i, int L, int nf, int hop, int h
 // the overlap-add, no thread holds prefetched spectra in registers across those phases, and the gain phase
 // reads its bins with LDS instead of LDG + 64-bit address arithmetic.  !STAGED is the round-1 register
 // prefetch, kept for n_fft = 2048, whose tile would cost a resident CTA.
-template <int ALG, int LOG2N, bool STAGED, bool TV, bool GAM = false>
-__global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT > 200 ? CSE_ENH_MB_LARGE : CSE_ENH_MB_SMALL)) enhance_kernel(EnhanceArgs a) {
+//
+// The body is a device function of (arguments, block index) so that two entry points share it: enhance_kernel
+// (one noise-PSD group per launch, the block index is the grid's) and enhance_groups_kernel (several groups of
+// one instantiation per launch, each block finds its group first).
+template <int ALG, int LOG2N, bool STAGED, bool TV, bool GAM>
+__device__ __forceinline__ void enhance_body(const EnhanceArgs& a, const int bx) {
     typedef EnhanceCfg<LOG2N> C;
     constexpr int NFFT = C::NFFT, M = C::M, LOG2M = LOG2N - 1, NTB = C::NTB, PPT = C::PPT, NT = C::NT, F = C::F;
     constexpr int XST = C::XST;
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
     const int W = NFFT + (F - 1) * hop;
     real* wsteady = ring + W;                                          // hop: steady-state window sum-of-squares
     const int tid = threadIdx.x;
-    const int item = a.item_list ? a.item_list[blockIdx.x] : a.item0 + blockIdx.x;
+    const int item = a.item_list ? a.item_list[bx] : a.item0 + bx;
     const int u = item / a.n_params, c = item - u * a.n_params;
     const int nbp = cse_nbp(NFFT);
     const int nf = a.n_frames, L = a.L;
@@ -291,7 +295,7 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
 
     const real2* __restrict__ Yu = a.Y + (size_t)u * nf * nbp;
     const real* __restrict__ Nu = a.N + (size_t)u * (TV ? (size_t)nf * nbp : (size_t)nbp);
-    real* __restrict__ out = a.out + (size_t)blockIdx.x * L;
+    real* __restrict__ out = a.out + (size_t)bx * L;
 
     const bool is_pair = tid < NTB, is_mid = tid == NTB;       // lane 0 of the extra warp: bin M/2
     const int n_slots = is_pair ? PPT : (is_mid ? 1 : 0);
@@ -561,6 +565,44 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
         while (raddr >= rend) raddr -= (unsigned)(W * sizeof(real));
         __syncthreads();
     }
+}
+
+
+
+template <int ALG, int LOG2N, bool STAGED, bool TV, bool GAM = false>
+__global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT > 200 ? CSE_ENH_MB_LARGE : CSE_ENH_MB_SMALL)) enhance_kernel(EnhanceArgs a) {
+    enhance_body<ALG, LOG2N, STAGED, TV, GAM>(a, (int)blockIdx.x);
+}
+
+// Several noise-PSD groups of ONE instantiation (algorithm, n_fft, kind of noise input) in one launch: the groups of a
+// small batch - one pair is the reference's own call pattern - are a dozen to a few hundred candidates each, far below
+// a wave; launched together they fill the GPU.  The descriptors travel as kernel parameters (no device copy, no
+// lifetime to manage); a block finds its group by a scan over at most CSE_ENH_MAX_GROUPS first-block indices (uniform).
+#define CSE_ENH_MAX_GROUPS 24
+struct EnhanceGroup {
+    const real2* Y;
+    const real* N;
+    const cse_params* params;
+    real* out;                       // [n_utts * n_params][L] of this group
+    int hop, n_frames, hop_shift, n_params, first_block, reserved;
+};
+struct EnhanceGroupsArgs {
+    const CseTables* T;
+    int noise_tv, L, n_groups;
+    real eps;
+    EnhanceGroup g[CSE_ENH_MAX_GROUPS];
+};
+template <int ALG, int LOG2N, bool STAGED, bool TV, bool GAM = false>
+__global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT > 200 ? CSE_ENH_MB_LARGE : CSE_ENH_MB_SMALL)) enhance_groups_kernel(EnhanceGroupsArgs ga) {
+    int gi = 0;
+    for (int k = 1; k < ga.n_groups; ++k)
+        if ((int)blockIdx.x >= ga.g[k].first_block) gi = k;
+    const EnhanceGroup& g = ga.g[gi];
+    EnhanceArgs a;
+    a.T = ga.T; a.Y = g.Y; a.N = g.N; a.params = g.params; a.out = g.out; a.item_list = nullptr;
+    a.noise_tv = ga.noise_tv; a.L = ga.L; a.hop = g.hop; a.n_frames = g.n_frames; a.n_params = g.n_params; a.item0 = 0;
+    a.hop_shift = g.hop_shift; a.eps = ga.eps;
+    enhance_body<ALG, LOG2N, STAGED, TV, GAM>(a, (int)blockIdx.x - g.first_block);
 }
 
 

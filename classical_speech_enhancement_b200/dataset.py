@@ -163,8 +163,7 @@ def run_dataset(pairs, out_dirs, summary_dir, *, algorithms=None, resume=False, 
             clean = np.stack([prepared[s][0] for s in stems])
             noisy = np.stack([prepared[s][1] for s in stems])
             chunk = PESQ_CHUNK_ITEMS if scorer is not None else None
-            eng = SweepEngine(clean, noisy, sr=target_sr, **({"chunk_items": chunk} if chunk else {}),
-                              **({"side_streams": 0} if stream is not None else {}))
+            eng = SweepEngine(clean, noisy, sr=target_sr, **({"chunk_items": chunk} if chunk else {}))
             base = eng.baseline_device()
             base_pesq = [None] * len(stems)
             if scorer is not None:

@@ -34,13 +34,11 @@ _runtime = {"lib": None, "backend_factory": None, "reuse_result_buffers": False,
             # share the candidate-invariant front of the Wiener / MMSE / Log-MMSE gain rules (cse_gamma) across a group
             "gamma": os.environ.get("CSE_GAMMA", "1") != "0",
             # a single pair: all groups of a grid scored by one align + one STOI launch (sweep_device)
-            "fuse_single": os.environ.get("CSE_FUSE_SINGLE", "1") != "0",
-            # ... and its groups' enhance launches spread over this many side streams (0: all on the current stream)
-            "fuse_streams": int(os.environ.get("CSE_FUSE_STREAMS", "4"))}
+            # and the groups of one kernel instantiation enhanced by one launch (cse_enhance_groups)
+            "fuse_single": os.environ.get("CSE_FUSE_SINGLE", "1") != "0"}
 _PLAN_CACHE = OrderedDict()      # (algorithm, grid digest, frame-count signature) -> host-side launch plan, LRU
 _PLAN_CACHE_MAX = 32
 _PINNED_POOL = {}
-_SIDE_STREAMS = {}              # (device index, id of the stream they fork from) -> [(torch stream, raw handle)]
 _TABLES_CACHE = {}               # (library, device) -> constant tables buffer (twiddles, windows, resampler taps)
 
 
@@ -132,32 +130,6 @@ class TorchCudaBackend:
     def synchronize(self):
         self.torch.cuda.current_stream(self.device).synchronize()
 
-    # --- fork / join over side streams: independent small launches of ONE engine side by side
-    def side_streams(self, n):
-        """``n`` side streams belonging to the CURRENT stream of this device (process-wide, persistent: engines that
-        work on the same stream share them, engines on different streams - the buckets a corpus driver keeps in
-        flight - never do, or their forks and joins would chain them to each other) -> (stream objects, handles)."""
-        pool = _SIDE_STREAMS.setdefault((self._dev_index, self._current_stream_id(self._dev_index)[0]), [])
-        while len(pool) < n:
-            st = self.torch.cuda.Stream(device=self.device)
-            pool.append((st, ctypes.c_void_p(st.cuda_stream)))
-        return [p[0] for p in pool[:n]], [p[1] for p in pool[:n]]
-
-    def fork(self, streams):
-        """The side streams wait for everything enqueued so far on the current stream."""
-        ev = self.torch.cuda.Event()
-        ev.record(self.torch.cuda.current_stream(self.device))
-        for st in streams:
-            st.wait_event(ev)
-
-    def join(self, streams):
-        """The current stream waits for everything enqueued so far on the side streams."""
-        cur = self.torch.cuda.current_stream(self.device)
-        for st in streams:
-            ev = self.torch.cuda.Event()
-            ev.record(st)
-            cur.wait_event(ev)
-
     def event(self):
         e = self.torch.cuda.Event(enable_timing=True)
         e.record(self.torch.cuda.current_stream(self.device))
@@ -236,8 +208,7 @@ def _synchronize_all(be):
 class SweepEngine:
     """One batch of ``U`` equal-length (clean, noisy) pairs resident on one device."""
 
-    def __init__(self, clean, noisy, sr=SR, lib=None, backend=None, chunk_items=DEFAULT_CHUNK_ITEMS, prepare_scoring=True,
-                 side_streams=None):
+    def __init__(self, clean, noisy, sr=SR, lib=None, backend=None, chunk_items=DEFAULT_CHUNK_ITEMS, prepare_scoring=True):
         if sr != SR:
             raise ValueError("the sweep runs at 16 kHz (the reference resamples every pair to 16 kHz first)")
         self.lib = lib if lib is not None else (_runtime["lib"] or _lib.load())
@@ -250,9 +221,6 @@ class SweepEngine:
         if clean.shape != noisy.shape or clean.ndim != 2:
             raise ValueError("clean and noisy must both be [U, L]")
         self.U, self.L = clean.shape
-        # one-pair engines spread their groups' launches over side streams (sweep_device) - unless a corpus driver
-        # already keeps several engines in flight on streams of their own (measured: the two do not add up)
-        self.side_streams = int(_runtime.get("fuse_streams") or 0) if side_streams is None else int(side_streams)
         if self.has_clean and prepare_scoring and self.L > self.lib.max_score_length(sr):
             raise _lib.CseError(_lib.CSE_EUNSUPPORTED, f"utterances of {self.L} samples exceed the scoring kernels' limit of "
                                 f"{self.lib.max_score_length(sr)} samples (about 38 s at 16 kHz); split the recording")
@@ -311,9 +279,6 @@ class SweepEngine:
         if getattr(self, "_timing", None) is None or not hasattr(self.be, "event"):
             return None
         return self.be.event()
-
-    def _timing_off(self):
-        return getattr(self, "_timing", None) is None
 
     def _record(self, tag, n_items, e0, e1):
         if e0 is not None:
@@ -535,25 +500,25 @@ class SweepEngine:
         if fused:
             wav_all = self._workspace("wav", pl["unique"] * self.L * rb)
             t_first = self._tick()
-            # the groups are independent and write disjoint slices: their (small) launches go round-robin onto side
-            # streams - forked after the spectrograms / noise PSDs they read are enqueued, joined before the scoring
             inputs = []
             for g in pl["groups"]:
                 Y = self.stft(g["key"][0], g["key"][1])
                 inputs.append((Y,) + ((self.gamma(g["key"]), 2) if pl.get("gamma") else self.noise(g["key"])))
-            n_side = self.side_streams if hasattr(be, "side_streams") and self._timing_off() else 0
-            side, handles = be.side_streams(n_side) if n_side > 1 else ([], [be.stream()])
-            if side:
-                be.fork(side)
-            p_tab = be.ptr(self.tables)
+            # ... and the groups of one kernel instantiation (n_fft, kind of noise input) go out as ONE launch
+            buckets = {}
             for gi, g in enumerate(pl["groups"]):
-                Y, N, tv = inputs[gi]
-                lib_.enhance_items(p_tab, alg, be.ptr(Y), be.ptr(N), int(tv), self.L, g["key"][0], g["key"][1],
-                                   be.ptr(dev["params"][gi]), g["n_rows"], 0, g["n_rows"],
-                                   be.ptr_at(wav_all, g["col0"] * self.L * rb), handles[gi % len(handles)])
-            self.launches += len(pl["groups"])
-            if side:
-                be.join(side)
+                buckets.setdefault((g["key"][0], int(inputs[gi][2])), []).append(gi)
+            for (n_fft, tv), members in buckets.items():
+                descs = (_lib.EnhanceGroup * len(members))()
+                for d, gi in zip(descs, members):
+                    g = pl["groups"][gi]
+                    d.Y, d.N = be.ptr(inputs[gi][0]).value, be.ptr(inputs[gi][1]).value
+                    d.params = be.ptr(dev["params"][gi]).value
+                    d.out = be.ptr_at(wav_all, g["col0"] * self.L * rb).value
+                    d.hop, d.n_params = g["key"][1], g["n_rows"]
+                lib_.enhance_groups(be.ptr(self.tables), alg, tv, 1, self.L, n_fft, ctypes.cast(descs, ctypes.c_void_p),
+                                    len(members), be.stream())
+                self.launches += -(-len(members) // 24)
         for gi, g in enumerate(() if fused else pl["groups"]):
             key = g["key"]
             n_fft, hop = key[0], key[1]

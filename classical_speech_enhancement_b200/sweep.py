@@ -213,7 +213,7 @@ def sweep_pairs(pairs, grids=DEFAULT_GRIDS, sr=16000, select=True, chunk_items=D
     def enqueue(idx, stream):
         with on(stream):
             eng = SweepEngine(np.stack([pairs[i][0] for i in idx]), np.stack([pairs[i][1] for i in idx]), sr=sr,
-                              chunk_items=chunk_items, **dict({"side_streams": 0} if stream is not None else {}, **(engine_kwargs or {})))
+                              chunk_items=chunk_items, **(engine_kwargs or {}))
             items = run_engine_device(eng, grids)
             dev_w = select_winners_device(eng, items) if select else None
         return eng, items, dev_w, stream

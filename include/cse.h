@@ -164,6 +164,20 @@ int cse_enhance_items(const void* tables, int algorithm, const void* Y, const vo
 int cse_enhance_list(const void* tables, int algorithm, const void* Y, const void* N, int noise_tv,
                      int length, int n_fft, int hop, const cse_params* params, int n_params,
                      const int* items, int n_items, void* out, void* stream);
+/* Grouped form: several noise-PSD groups of ONE (algorithm, n_fft, noise_tv) in one launch - for small batches (one
+ * pair is the reference's own call pattern, Code/speech_enhancement_comparison.py:108-252), whose groups are far
+ * smaller than the GPU.  Group k computes all n_utts * n_params candidates of its (Y, N, params, hop) into its own
+ * `out` [n_utts * n_params][length].  `groups` is a HOST array (copied into the launch parameters). */
+typedef struct cse_enhance_group {
+    const void* Y;            /* [dev] as for cse_enhance, shape of (n_fft, hop) */
+    const void* N;            /* [dev] noise PSD or a-posteriori SNR, as noise_tv says */
+    const cse_params* params; /* [dev] n_params rows */
+    void* out;                /* [dev] [n_utts * n_params][length] */
+    int hop;
+    int n_params;
+} cse_enhance_group;
+int cse_enhance_groups(const void* tables, int algorithm, int noise_tv, int n_utts, int length, int n_fft,
+                       const cse_enhance_group* groups, int n_groups, void* stream);
 int cse_score_items(const void* tables, const void* wav, int item0, int n_items, int per_utt,
                     int length, int sr, const void* clean, const void* cache, int finalize,
                     cse_score_t* scores, void* workspace, size_t workspace_bytes, void* stream);

@@ -17,6 +17,7 @@
 #include "../../classical_speech_enhancement_b200/csrc/cse_lib.cu"
 
 #include <cassert>
+#include <cstring>
 #include <vector>
 
 static std::vector<real> make_signal(int L, unsigned seed, const std::vector<real>* base, real noise) {
@@ -98,6 +99,17 @@ static int run_case(int L, int nan_at) {
                 std::vector<real> out((size_t)2 * L);
                 CHECK(cse_enhance_list(tables.data(), alg, Y.data(), nz.N, nz.tv, L, n_fft, hop, rows[alg], n_params, items, 2,
                                        out.data(), nullptr));
+                {   // grouped launch: two groups (the same inputs twice, second with one row) == cse_enhance of each
+                    std::vector<real> ref((size_t)U * n_params * L), g0((size_t)U * n_params * L), g1((size_t)U * L);
+                    CHECK(cse_enhance(tables.data(), alg, Y.data(), nz.N, nz.tv, U, L, n_fft, hop, rows[alg], n_params, ref.data(), nullptr));
+                    cse_enhance_group gr[2] = {{Y.data(), nz.N, rows[alg], g0.data(), hop, n_params},
+                                               {Y.data(), nz.N, rows[alg], g1.data(), hop, 1}};
+                    CHECK(cse_enhance_groups(tables.data(), alg, nz.tv, U, L, n_fft, gr, 2, nullptr));
+                    bool same = memcmp(ref.data(), g0.data(), ref.size() * sizeof(real)) == 0;
+                    for (int u = 0; u < U && same; ++u)
+                        same = memcmp(&ref[(size_t)u * n_params * L], &g1[(size_t)u * L], (size_t)L * sizeof(real)) == 0;
+                    if (!same) { fprintf(stderr, "grouped launch differs: alg %d\n", alg); return 1; }
+                }
                 for (int u = 0; u < U; ++u)
                     for (int c = 0; c < n_params; ++c) {
                         const cse_score_t& s = scores[(size_t)u * n_params + c];

@@ -1,6 +1,6 @@
 """Where the device time of ONE pair goes (fresh engine per repetition, all four full grids): engine set-up, the groups'
 enhance launches (incl. the spectrograms / noise PSDs / a-posteriori SNRs they need), alignment, STOI - against the same
-work at the large-batch rates.  python tools/pair_timeline.py [--streams N]"""
+work at the large-batch rates.  python tools/pair_timeline.py"""
 import os
 import sys
 import warnings
@@ -14,7 +14,6 @@ from classical_speech_enhancement_b200.sweep import DEFAULT_GRIDS, cached_points
 from classical_speech_enhancement_b200.synth import make_pair  # noqa: E402
 
 warnings.filterwarnings("ignore")
-streams = int(sys.argv[sys.argv.index("--streams") + 1]) if "--streams" in sys.argv else 4
 
 
 def ev():
@@ -29,7 +28,7 @@ for rep in range(reps + 2):
     c, n = make_pair(100 + rep, 48000)
     torch.cuda.synchronize()
     marks = [("start", ev())]
-    eng = SweepEngine(c[None].astype(np.float32), n[None].astype(np.float32), side_streams=streams)
+    eng = SweepEngine(c[None].astype(np.float32), n[None].astype(np.float32))
     marks.append(("engine: H2D, clean-side caches", ev()))
     for name, ranges in DEFAULT_GRIDS:
         table, pl = eng.sweep_device(name, cached_points(name, ranges))
