@@ -46,6 +46,7 @@ SIGNATURES = {
     "cse_enhance_items": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp, _vp]),
     "cse_enhance_list": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "cse_enhance_groups": (_i, [_vp, _i, _i, _i, _i, _i, _vp, _i, _vp]),
+    "cse_gamma_groups": (_i, [_i, _i, _i, _vp, _i, _vp]),
     "cse_score_items": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "cse_align_items": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
     "cse_stoi_items": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _sz, _vp]),
@@ -64,6 +65,11 @@ WINNER_DTYPE = np.dtype([("index", np.int32), ("lag", np.int32), ("flags", np.in
 class EnhanceGroup(ctypes.Structure):
     """``cse_enhance_group`` (include/cse.h): one noise-PSD group of a grouped enhance launch."""
     _fields_ = [("Y", _vp), ("N", _vp), ("params", _vp), ("out", _vp), ("hop", _i), ("n_params", _i)]
+
+
+class GammaGroup(ctypes.Structure):
+    """``cse_gamma_group`` (include/cse.h)."""
+    _fields_ = [("Y", _vp), ("N", _vp), ("G", _vp), ("noise_tv", _i), ("hop", _i), ("noise_mu", _d), ("eps", _d)]
 
 
 class CseLibraryError(RuntimeError):

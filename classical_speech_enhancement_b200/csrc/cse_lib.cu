@@ -211,6 +211,35 @@ extern "C" int cse_gamma(const void* Y, const void* N, int noise_tv, int n_utts,
     return check_launch("gamma_kernel");
 }
 
+extern "C" int cse_gamma_groups(int n_utts, int length, int n_fft, const cse_gamma_group* groups, int n_groups, void* stream) {
+    CSE_REQUIRE(groups, "NULL argument");
+    CSE_REQUIRE(valid_nfft(n_fft) && n_utts > 0 && n_groups > 0 && length > n_fft / 2, "bad sizes");
+    const int nb = n_fft / 2 + 1, nbp = cse_nbp(n_fft);
+    for (int k = 0; k < n_groups; ++k) {
+        CSE_REQUIRE(groups[k].Y && groups[k].N && groups[k].G, "NULL argument in group %d", k);
+        CSE_REQUIRE(groups[k].hop > 0, "bad hop in group %d", k);
+        CSE_REQUIRE(groups[k].noise_tv == 0 || groups[k].noise_tv == 1, "noise_tv must be 0 (static PSD) or 1 (time-varying PSD)");
+    }
+    for (int g0 = 0; g0 < n_groups; g0 += CSE_GAMMA_MAX_GROUPS) {
+        GammaGroupsArgs ga;
+        ga.nb = nb; ga.nbp = nbp;
+        const int n = n_groups - g0 < CSE_GAMMA_MAX_GROUPS ? n_groups - g0 : CSE_GAMMA_MAX_GROUPS;
+        for (int k = 0; k < CSE_GAMMA_MAX_GROUPS; ++k) {
+            const cse_gamma_group& src = groups[g0 + (k < n ? k : 0)];
+            GammaGroup& g = ga.g[k];
+            g.Y = (const real2*)src.Y; g.N = (const real*)src.N; g.out = (real*)src.G; g.noise_tv = src.noise_tv;
+            g.nf = cse_num_frames(length, src.hop);
+            real mu = (real)src.noise_mu;
+            if (src.noise_mu >= 0.0) mu = r_clip(mu, R(0), R(0.9999));           // mmse.py:51, advanced_mmse.py:61
+            g.mu = mu; g.eps = (real)src.eps;
+        }
+        CSE_LAUNCH(gamma_groups_kernel, dim3((nbp + 127) / 128, n_utts, n), 128, 0, stream, ga);
+        const int rc = check_launch("gamma_groups_kernel");
+        if (rc != CSE_OK) return rc;
+    }
+    return CSE_OK;
+}
+
 extern "C" int cse_enhance_list(const void* tables, int algorithm, const void* Y, const void* N, int noise_tv, int length,
                                 int n_fft, int hop, const cse_params* params, int n_params, const int* items, int n_items,
                                 void* out, void* stream) {

@@ -612,9 +612,8 @@ __global__ void __launch_bounds__(EnhanceCfg<LOG2N>::NT, (EnhanceCfg<LOG2N>::NT 
 //   gamma(t) = max(|Y(t)|^2 / N'(t), eps)            (a-posteriori SNR: wiener_filter.py:61, mmse.py:67, advanced_mmse.py:76)
 // One thread per (utterance, bin) walks the frames; a warp reads 32 neighbouring bins of a frame (coalesced).
 // Same operations, in the same order, as gain_pair<..., GAM = false>.
-__global__ void __launch_bounds__(128) gamma_kernel(const real2* __restrict__ Y, const real* __restrict__ N, int noise_tv, int nf,
-                                                    int nb, int nbp, real mu, real eps, real* __restrict__ out) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x, u = blockIdx.y;
+CSE_D void gamma_body(const real2* __restrict__ Y, const real* __restrict__ N, int noise_tv, int nf, int nb, int nbp, real mu,
+                      real eps, real* __restrict__ out, const int k, const int u) {
     if (k >= nbp) return;
     const real2* __restrict__ Yu = Y + (size_t)u * nf * nbp + k;
     const real* __restrict__ Nu = N + (size_t)u * (noise_tv ? (size_t)nf * nbp : (size_t)nbp) + k;
@@ -625,12 +624,14 @@ __global__ void __launch_bounds__(128) gamma_kernel(const real2* __restrict__ Y,
     const real nstat = noise_tv ? R(0) : r_max(Nu[0], eps);
     const real rstat = noise_tv ? R(0) : r_rcp(nstat);
     real nsm = R(0);
-    for (int t = 0; t < nf; ++t) {
-        const real2 y = Yu[(size_t)t * nbp];
+    // eight frames' loads are issued before their (sequential) use: the chain is bound by memory latency, and after
+    // inlining into the grouped entry point the compiler no longer batches the loads by itself
+    constexpr int UF = 8;
+    auto step = [&](int t, real2 y, real nraw) {
         const real pw = r_fma(y.x, y.x, y.y * y.y);
         real g;
         if (noise_tv) {
-            real nt = r_max(Nu[(size_t)t * nbp], eps);
+            real nt = r_max(nraw, eps);
             if (smooth) {
                 if (t > 0) nt = r_fma(mu, nsm, one_minus_mu * nt);
                 nsm = nt;
@@ -639,5 +640,42 @@ __global__ void __launch_bounds__(128) gamma_kernel(const real2* __restrict__ Y,
             g = pw * r_rcp(nt);
         } else g = pw * rstat;
         o[(size_t)t * nbp] = r_max(g, eps);
+    };
+    int t = 0;
+    for (; t + UF <= nf; t += UF) {
+        real2 y[UF];
+        real nn[UF];
+#pragma unroll
+        for (int j = 0; j < UF; ++j) {
+            y[j] = __ldg(Yu + (size_t)(t + j) * nbp);
+            nn[j] = noise_tv ? __ldg(Nu + (size_t)(t + j) * nbp) : R(0);
+        }
+#pragma unroll
+        for (int j = 0; j < UF; ++j) step(t + j, y[j], nn[j]);
     }
+    for (; t < nf; ++t) step(t, __ldg(Yu + (size_t)t * nbp), noise_tv ? __ldg(Nu + (size_t)t * nbp) : R(0));
+}
+
+__global__ void __launch_bounds__(128) gamma_kernel(const real2* __restrict__ Y, const real* __restrict__ N, int noise_tv, int nf,
+                                                    int nb, int nbp, real mu, real eps, real* __restrict__ out) {
+    gamma_body(Y, N, noise_tv, nf, nb, nbp, mu, eps, out, (int)(blockIdx.x * blockDim.x + threadIdx.x), (int)blockIdx.y);
+}
+
+// Several (noise PSD, noise_mu) groups of one n_fft in one launch (blockIdx.z = group): a single pair needs ~36 of them,
+// each a chain of n_frames dependent steps on 513 threads - one after the other they cost more than the gain kernels.
+#define CSE_GAMMA_MAX_GROUPS 32
+struct GammaGroup {
+    const real2* Y;
+    const real* N;
+    real* out;
+    int noise_tv, nf;
+    real mu, eps;
+};
+struct GammaGroupsArgs {
+    int nb, nbp;
+    GammaGroup g[CSE_GAMMA_MAX_GROUPS];
+};
+__global__ void __launch_bounds__(128) gamma_groups_kernel(GammaGroupsArgs ga) {
+    const GammaGroup& g = ga.g[blockIdx.z];
+    gamma_body(g.Y, g.N, g.noise_tv, g.nf, ga.nb, ga.nbp, g.mu, g.eps, g.out, (int)(blockIdx.x * blockDim.x + threadIdx.x), (int)blockIdx.y);
 }

@@ -382,6 +382,29 @@ class SweepEngine:
             self._gamma[key6] = G
         return self._gamma[key6]
 
+    def gamma_many(self, keys6):
+        """The missing ones of ``keys6`` by one ``cse_gamma_groups`` launch per n_fft (a one-pair sweep needs ~36 of
+        them; one by one their dependent frame chains are the longest part of its device time)."""
+        missing = [k for k in dict.fromkeys(keys6) if k not in self._gamma]
+        if len(missing) < 2:
+            return
+        be = self.be
+        by_nfft = {}
+        for k in missing:
+            by_nfft.setdefault(k[0], []).append(k)
+        for n_fft, ks in by_nfft.items():
+            descs = (_lib.GammaGroup * len(ks))()
+            for d, k6 in zip(descs, ks):
+                key, mu = k6[:5], k6[5]
+                Y = self.stft(n_fft, key[1])
+                N, tv = self.noise(key)
+                G = be.empty((self.U, self.n_frames(n_fft, key[1]), self.lib.bins_padded(n_fft)), self.real)
+                d.Y, d.N, d.G = be.ptr(Y).value, be.ptr(N).value, be.ptr(G).value
+                d.noise_tv, d.hop, d.noise_mu, d.eps = int(tv), key[1], -1.0 if mu is None else float(mu), float(key[4])
+                self._gamma[k6] = G
+            self.lib.gamma_groups(self.U, self.L, n_fft, ctypes.cast(descs, ctypes.c_void_p), len(ks), be.stream())
+            self.launches += -(-len(ks) // 32)
+
     def drop_caches(self):
         self._stft.clear()
         self._pow.clear()
@@ -501,6 +524,8 @@ class SweepEngine:
             wav_all = self._workspace("wav", pl["unique"] * self.L * rb)
             t_first = self._tick()
             inputs = []
+            if pl.get("gamma"):
+                self.gamma_many([g["key"] for g in pl["groups"]])
             for g in pl["groups"]:
                 Y = self.stft(g["key"][0], g["key"][1])
                 inputs.append((Y,) + ((self.gamma(g["key"]), 2) if pl.get("gamma") else self.noise(g["key"])))

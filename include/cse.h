@@ -117,6 +117,18 @@ int cse_noise_mintrack(const void* P, int n_utts, int n_frames, int n_fft, doubl
  * of N with noise_tv = 2 (and ignore the candidates' noise_mu): hundreds of candidates then share this work. */
 int cse_gamma(const void* Y, const void* N, int noise_tv, int n_utts, int length, int n_fft, int hop,
               double noise_mu, double eps, void* G, void* stream);
+/* Grouped form: several (noise PSD, noise_mu) combinations of ONE n_fft in one launch (a single pair needs about 36;
+ * launched one by one their dependent frame chains cost more than the gain kernels).  `groups` is a HOST array. */
+typedef struct cse_gamma_group {
+    const void* Y;      /* [dev] spectrogram of (n_fft, hop) */
+    const void* N;      /* [dev] noise PSD as noise_tv says (0 / 1) */
+    void* G;            /* [dev] [U][nf][nbp] */
+    int noise_tv;
+    int hop;
+    double noise_mu;    /* < 0: no smoothing */
+    double eps;
+} cse_gamma_group;
+int cse_gamma_groups(int n_utts, int length, int n_fft, const cse_gamma_group* groups, int n_groups, void* stream);
 
 /* Gain + ISTFT for n_utts x n_params candidates (utterance-major): out[(u*n_params+c)][L].
  * noise_tv: 0 -> N is [U][nbp] (static), 1 -> N is [U][nf][nbp] (time-varying), 2 -> N is the a-posteriori SNR

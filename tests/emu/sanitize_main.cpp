@@ -86,6 +86,16 @@ static int run_case(int L, int nan_at) {
                     std::vector<cse_score_t> scores2((size_t)U * n_params);
                     const double mu = (alg == 2) ? rows[alg][0].v[4] : (alg == 3 ? rows[alg][0].v[3] : -1.0);
                     CHECK(cse_gamma(Y.data(), nz.N, nz.tv, U, L, n_fft, hop, nz.tv ? mu : -1.0, alg == 2 ? 1e-12 : 1e-10, G.data(), nullptr));
+                    {   // grouped form: the same gamma twice in one launch == cse_gamma
+                        std::vector<real> Ga((size_t)U * nf * nbp), Gb((size_t)U * nf * nbp);
+                        const double e = alg == 2 ? 1e-12 : 1e-10, m = nz.tv ? mu : -1.0;
+                        cse_gamma_group gg[2] = {{Y.data(), nz.N, Ga.data(), nz.tv, hop, m, e}, {Y.data(), nz.N, Gb.data(), nz.tv, hop, m, e}};
+                        CHECK(cse_gamma_groups(U, L, n_fft, gg, 2, nullptr));
+                        if (memcmp(G.data(), Ga.data(), G.size() * sizeof(real)) || memcmp(G.data(), Gb.data(), G.size() * sizeof(real))) {
+                            fprintf(stderr, "grouped gamma differs: alg %d\n", alg);
+                            return 1;
+                        }
+                    }
                     CHECK(cse_sweep(tables.data(), alg, Y.data(), G.data(), 2, U, L, n_fft, hop, rows[alg], 1, sr, clean.data(),
                                     cache.data(), scores2.data(), chunk, ws.data(), ws.size(), nullptr));
                     for (int u = 0; u < U; ++u)
