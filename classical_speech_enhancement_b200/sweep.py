@@ -196,6 +196,8 @@ def sweep_pairs(pairs, grids=DEFAULT_GRIDS, sr=16000, select=True, chunk_items=D
         if c.ndim != 1 or c.shape != n.shape:
             raise ValueError(f"pair {i}: clean and noisy must be 1-D arrays of equal length")
         by_len.setdefault(len(c), []).append(i)
+    if not by_len:
+        raise ValueError("sweep_pairs needs at least one (clean, noisy) pair")
     # longest first: every later bucket fits the blocks the caching allocator already holds (ascending order would
     # ask for a slightly larger block each time - a cudaMalloc, and its device-wide synchronisation, per bucket)
     buckets = [idx for _, idx in sorted(by_len.items(), reverse=True)]
