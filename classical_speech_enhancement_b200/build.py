@@ -56,7 +56,7 @@ def build_cuda(fp64=False, force=False, verbose=False):
            "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(ROOT, "include")]
     if fp64:
         cmd.append("-DCSE_FP64")
-    tmp = target + ".part"                 # built aside and renamed: a reader (or a repository snapshot) never sees half a library
+    tmp = f"{target}.part.{os.getpid()}"   # built aside and renamed: a reader (or a repository snapshot) never sees half a library
     cmd += SOURCES + ["-o", tmp]
     out = _run(cmd, log=os.path.join(PKG, "build_fp64.log" if fp64 else "build.log"))
     os.replace(tmp, target)
@@ -78,7 +78,7 @@ def build_emu(fp64=False, force=False):
            "-I", os.path.join(ROOT, "tests", "emu"), "-I", os.path.join(ROOT, "include")]
     if fp64:
         cmd.append("-DCSE_FP64")
-    tmp = target + ".part"
+    tmp = f"{target}.part.{os.getpid()}"       # per process: two builders (the ranks of a multi-process test) never share a file
     cmd += SOURCES + ["-o", tmp]
     _run(cmd)
     os.replace(tmp, target)

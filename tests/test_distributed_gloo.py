@@ -63,6 +63,8 @@ def test_two_rank_gloo_equals_single_process():
     from classical_speech_enhancement_b200.synth import make_batch
     from classical_speech_enhancement_b200.sweep import sweep_dataset
     from tests.emu_util import use_emulated_runtime, use_product_runtime
+    from classical_speech_enhancement_b200 import build
+    build.build_emu()                      # before the ranks start: they load it instead of compiling it side by side
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
